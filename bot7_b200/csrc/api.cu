@@ -1,0 +1,697 @@
+// C ABI of libbot7_b200.so: handles, host<->device plumbing, jitter-retry policy, panel loop.
+// See include/bot7_b200.h for the contract and the reference interface each entry replaces.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "b7_internal.h"
+
+static thread_local char g_err[512] = "";
+
+void b7_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int b7_score_grid_size(b7_ctx* ctx, int64_t M);   // score.cu
+
+namespace {
+
+constexpr int kParStride = B7_MAX_DIMS + 4;
+constexpr double kLog2Pi = 1.83787706640934548356;
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    b7_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return B7_ERR_NOMEM;
+  }
+  return 0;
+}
+
+int grow(double** p, size_t* have, size_t need_bytes) {
+  if (*have >= need_bytes) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  cudaError_t e = cudaMalloc((void**)p, need_bytes);
+  if (e != cudaSuccess) { b7_set_error("cudaMalloc of %zu bytes failed: %s", need_bytes, cudaGetErrorString(e)); return B7_ERR_NOMEM; }
+  *have = need_bytes;
+  return 0;
+}
+
+inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
+
+// candidates per posterior launch: one 128-candidate tile per SM = one full wave
+inline int64_t panel_rows(b7_ctx* ctx) { return (int64_t)ctx->sm_count * 128; }
+
+int sync_removed(b7_grid* g) {
+  if (!g->removed_dirty) return 0;
+  int64_t n = (int64_t)g->removed.size();
+  if (n > g->removed_cap) {
+    if (g->removed_dev) cudaFree(g->removed_dev);
+    g->removed_cap = std::max<int64_t>(256, 2 * n);
+    B7_CHECK(dev_alloc(&g->removed_dev, (size_t)g->removed_cap));
+  }
+  if (n > 0)
+    B7_CUDA(cudaMemcpyAsync(g->removed_dev, g->removed.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, g->ctx->stream));
+  g->removed_dirty = false;
+  return 0;
+}
+
+__global__ void frob_rows_kernel(const double* __restrict__ A, int Np, int N, double* __restrict__ out) {
+  // sum of squares of row blockIdx.x (first N columns), fixed-order tree
+  __shared__ double sh[256];
+  double s = 0.0;
+  const double* row = A + (long long)blockIdx.x * Np;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) s += row[k] * row[k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+__global__ void identity_kernel(double* __restrict__ A, int Np) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (long long)Np * Np) A[e] = (e / Np == e % Np) ? 1.0 : 0.0;
+}
+
+int upload_residual(b7_gp* gp, int s, const std::vector<double>& yh) {
+  // r = y - m (padded with zeros) into beta[s]
+  std::vector<double> r((size_t)gp->Np, 0.0);
+  const double m = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 2];
+  for (int i = 0; i < gp->N; ++i) r[i] = yh[i] - m;
+  B7_CUDA(cudaMemcpyAsync(gp->beta + (size_t)s * gp->Np, r.data(), gp->Np * sizeof(double), cudaMemcpyHostToDevice, gp->ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  return 0;
+}
+
+int build_kxx(b7_gp* gp, int s0, int count) {
+  b7_ctx* ctx = gp->ctx;
+  StageTimer t(ctx, ST_KBUILD);
+  B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, gp->X, gp->N, gp->Np, gp->d, gp->Xt, gp->N, gp->Np,
+                                 gp->par + (size_t)s0 * kParStride, kParStride, gp->fac + (size_t)s0 * gp->Np * gp->Np,
+                                 (int64_t)gp->Np * gp->Np, count, true));
+  t.stop(1);
+  return 0;
+}
+
+int factor(b7_gp* gp, int s0, int count) {
+  b7_ctx* ctx = gp->ctx;
+  StageTimer t(ctx, ST_POTRF);
+  int64_t before = ctx->launches;
+  B7_CHECK(b7_launch_potrf(gp, s0, count));
+  t.stop((int)(ctx->launches - before));
+  return 0;
+}
+
+}  // namespace
+
+struct GpHostCopy { std::vector<double> y; };
+static std::vector<std::pair<b7_gp*, GpHostCopy*>> g_gp_host;   // y kept on the host for the retry path
+
+static GpHostCopy* host_copy(b7_gp* gp) {
+  for (auto& p : g_gp_host) if (p.first == gp) return p.second;
+  return nullptr;
+}
+
+extern "C" {
+
+int b7_version(void) { return 100; }
+const char* b7_last_error(void) { return g_err; }
+
+int b7_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b7_init(int device, b7_ctx** out) {
+  if (!out) { b7_set_error("b7_init: out is null"); return B7_ERR_ARG; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    b7_set_error("b7_init: no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    return B7_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { b7_set_error("b7_init: device %d out of range [0,%d)", device, n); return B7_ERR_ARG; }
+  B7_CUDA(cudaSetDevice(device));
+  b7_ctx* ctx = new b7_ctx();
+  ctx->device = device;
+  cudaDeviceProp p;
+  B7_CUDA(cudaGetDeviceProperties(&p, device));
+  ctx->sm_count = p.multiProcessorCount;
+  if (p.major < 10) { b7_set_error("b7_init: device is sm_%d%d, this build is sm_100a only", p.major, p.minor); delete ctx; return B7_ERR_CUDA; }
+  B7_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  B7_CUDA(cudaEventCreate(&ctx->ev0));
+  B7_CUDA(cudaEventCreate(&ctx->ev1));
+  *out = ctx;
+  return 0;
+}
+
+void b7_shutdown(b7_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ks) cudaFree(ctx->ks);
+  if (ctx->moments) cudaFree(ctx->moments);
+  if (ctx->xs_stage) cudaFree(ctx->xs_stage);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int b7_sync(b7_ctx* ctx) {
+  if (!ctx) return B7_ERR_ARG;
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b7_set_profiling(b7_ctx* ctx, int on) { if (!ctx) return B7_ERR_ARG; ctx->profiling = on != 0; return 0; }
+int b7_reset_stage_timers(b7_ctx* ctx) {
+  if (!ctx) return B7_ERR_ARG;
+  for (int i = 0; i < ST_COUNT; ++i) { ctx->stage_ms[i] = 0; ctx->stage_calls[i] = 0; }
+  return 0;
+}
+int b7_last_stage_ms(b7_ctx* ctx, int stage, double* ms_total, int64_t* launches) {
+  if (!ctx || stage < 0 || stage >= ST_COUNT) return B7_ERR_ARG;
+  if (ms_total) *ms_total = ctx->stage_ms[stage];
+  if (launches) *launches = ctx->stage_calls[stage];
+  return 0;
+}
+int64_t b7_launch_count(b7_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ------------------------------------------------------------------ grids */
+
+int b7_sobol_directions(int dims, uint32_t* out) {
+  if (dims < 1 || dims >= B7_MAX_DIMS || !out) { b7_set_error("sobol: dims must satisfy 1 <= dims < 40"); return B7_ERR_ARG; }
+  b7_sobol_directions_host(dims, out);
+  return 0;
+}
+
+int b7_sobol_generate(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, const double* mins,
+                      const double* maxes, double* out_host, b7_grid** out_grid) {
+  if (!ctx) return B7_ERR_ARG;
+  if (out_grid) *out_grid = nullptr;
+  // grids/sobol.lua:36 assert(dims < max_dims); :318-324 "Too many calls" beyond 2^30 points
+  if (dims < 1 || dims >= B7_MAX_DIMS) { b7_set_error("sobol: dims must satisfy 1 <= dims < 40"); return B7_ERR_ARG; }
+  if (first_seed < 0) first_seed = 0;   // grids/sobol.lua:291 seed = max(0, floor(seed))
+  if (count < 0 || first_seed + count > (1LL << B7_SOBOL_BITS)) { b7_set_error("sobol: too many calls (seed range exceeds 2^30)"); return B7_ERR_ARG; }
+  if ((mins == nullptr) != (maxes == nullptr)) { b7_set_error("sobol: one-sided rescaling is done by the host wrapper; pass both mins and maxes or neither"); return B7_ERR_ARG; }
+  B7_CUDA(cudaSetDevice(ctx->device));
+  double* dev = nullptr;
+  B7_CHECK(dev_alloc(&dev, (size_t)count * dims));
+  double *dmin = nullptr, *dscale = nullptr;
+  if (mins) {
+    double h[2 * B7_MAX_DIMS];
+    for (int i = 0; i < dims; ++i) { h[i] = mins[i]; h[B7_MAX_DIMS + i] = maxes[i] + (-mins[i]); }   // torch.add(maxes, -mins)
+    B7_CHECK(dev_alloc(&dmin, 2 * B7_MAX_DIMS));
+    dscale = dmin + B7_MAX_DIMS;
+    B7_CUDA(cudaMemcpyAsync(dmin, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  StageTimer t(ctx, ST_SOBOL);
+  int rc = b7_launch_sobol(ctx, dims, first_seed, count, dmin, dscale, dev);
+  t.stop(1);
+  if (rc == 0 && out_host && count > 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, dev, (size_t)count * dims * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) { b7_set_error("sobol D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc == 0 && e != cudaSuccess) { b7_set_error("sobol: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
+  if (dmin) cudaFree(dmin);
+  if (rc != 0 || !out_grid) { cudaFree(dev); return rc; }
+  b7_grid* g = new b7_grid();
+  g->ctx = ctx; g->rows = count; g->d = dims; g->X = dev;
+  *out_grid = g;
+  return 0;
+}
+
+int b7_grid_from_host(b7_ctx* ctx, const double* X, int64_t M, int d, b7_grid** out_grid) {
+  if (!ctx || !out_grid || M < 0 || d < 1 || (M > 0 && !X)) { b7_set_error("grid_from_host: bad arguments"); return B7_ERR_ARG; }
+  *out_grid = nullptr;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  double* dev = nullptr;
+  B7_CHECK(dev_alloc(&dev, (size_t)M * d));
+  if (M > 0) {
+    B7_CUDA(cudaMemcpyAsync(dev, X, (size_t)M * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  b7_grid* g = new b7_grid();
+  g->ctx = ctx; g->rows = M; g->d = d; g->X = dev;
+  *out_grid = g;
+  return 0;
+}
+
+int b7_grid_read(b7_grid* g, int64_t first_row, int64_t count, double* out_host) {
+  if (!g || first_row < 0 || count < 0 || first_row + count > g->rows || (count > 0 && !out_host)) { b7_set_error("grid_read: range"); return B7_ERR_ARG; }
+  B7_CUDA(cudaSetDevice(g->ctx->device));
+  if (count == 0) return 0;
+  B7_CUDA(cudaMemcpyAsync(out_host, g->X + first_row * g->d, (size_t)count * g->d * sizeof(double), cudaMemcpyDeviceToHost, g->ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  return 0;
+}
+
+int64_t b7_grid_size(b7_grid* g) { return g ? g->rows - (int64_t)g->removed.size() : 0; }
+int64_t b7_grid_rows(b7_grid* g) { return g ? g->rows : 0; }
+int b7_grid_dims(b7_grid* g) { return g ? g->d : 0; }
+
+// compacted 1-based index -> original 0-based row: the smallest r with r - #removed(<= r) == c-1
+static int64_t compacted_to_original(const b7_grid* g, int64_t c1) {
+  int64_t r = c1 - 1;
+  for (int64_t t : g->removed) {   // removed is sorted ascending
+    if (t <= r) ++r; else break;
+  }
+  return r;
+}
+
+int b7_grid_original_index(b7_grid* g, int64_t compacted_index, int64_t* original_index_1based) {
+  if (!g || compacted_index < 1 || compacted_index > b7_grid_size(g)) { b7_set_error("grid: compacted index out of range"); return B7_ERR_ARG; }
+  if (original_index_1based) *original_index_1based = compacted_to_original(g, compacted_index) + 1;
+  return 0;
+}
+
+int b7_grid_remove(b7_grid* g, int64_t compacted_index, double* removed_row) {
+  if (!g || compacted_index < 1 || compacted_index > b7_grid_size(g)) { b7_set_error("grid_remove: index out of range"); return B7_ERR_ARG; }
+  int64_t r = compacted_to_original(g, compacted_index);
+  if (removed_row) B7_CHECK(b7_grid_read(g, r, 1, removed_row));
+  g->removed.insert(std::upper_bound(g->removed.begin(), g->removed.end(), r), r);
+  g->removed_dirty = true;
+  return 0;
+}
+
+void b7_grid_free(b7_grid* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  if (g->X) cudaFree(g->X);
+  if (g->removed_dev) cudaFree(g->removed_dev);
+  delete g;
+}
+
+/* ------------------------------------------------------------------ GP */
+
+void b7_gp_free(b7_gp* gp) {
+  if (!gp) return;
+  cudaSetDevice(gp->ctx->device);
+  cudaStreamSynchronize(gp->ctx->stream);
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (size_t i = 0; i < g_gp_host.size(); ++i)
+    if (g_gp_host[i].first == gp) { delete g_gp_host[i].second; g_gp_host.erase(g_gp_host.begin() + i); break; }
+  delete gp;
+}
+
+int b7_gp_num_draws(b7_gp* gp) { return gp ? gp->S : 0; }
+int b7_gp_num_obs(b7_gp* gp) { return gp ? gp->N : 0; }
+int b7_gp_padded_n(b7_gp* gp) { return gp ? gp->Np : 0; }
+
+static int gp_retry_draw(b7_gp* gp, int s, int first_info);
+
+int b7_gp_fit_range(b7_gp* gp, int s0, int count, int* info, double* logml, double* jitter) {
+  if (!gp || s0 < 0 || count < 0 || s0 + count > gp->S) { b7_set_error("gp_fit_range: draw range"); return B7_ERR_ARG; }
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  if (count == 0) return 0;
+  B7_CHECK(build_kxx(gp, s0, count));
+  B7_CHECK(factor(gp, s0, count));
+  std::vector<int> inf((size_t)count);
+  B7_CUDA(cudaMemcpyAsync(inf.data(), gp->info + s0, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) {
+    gp->jitter[s0 + i] = 0.0;
+    gp->info_host[s0 + i] = 0;
+    if (inf[i] != 0) B7_CHECK(gp_retry_draw(gp, s0 + i, inf[i]));   // utils/math.lua:168-216
+  }
+  // log marginal likelihood: -1/2 beta^T beta - sum log L_ii - N/2 log 2pi  (r^T K^-1 r = |L^-1 r|^2)
+  std::vector<double> bh((size_t)count * gp->Np), ldh((size_t)count);
+  B7_CUDA(cudaMemcpyAsync(bh.data(), gp->beta + (size_t)s0 * gp->Np, bh.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B7_CUDA(cudaMemcpyAsync(ldh.data(), gp->logdet + s0, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) {
+    double q = 0.0;
+    for (int k = 0; k < gp->N; ++k) q += bh[(size_t)i * gp->Np + k] * bh[(size_t)i * gp->Np + k];
+    gp->logml_host[s0 + i] = -0.5 * q - ldh[i] - 0.5 * gp->N * kLog2Pi;
+  }
+  for (int i = 0; i < count; ++i) {
+    if (info) info[i] = gp->info_host[s0 + i];
+    if (logml) logml[i] = gp->logml_host[s0 + i];
+    if (jitter) jitter[i] = gp->jitter[s0 + i];
+  }
+  return 0;
+}
+
+// utils.math.chol retry policy (utils/math.lua:168-216) for one draw whose plain factorisation failed
+static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
+  b7_ctx* ctx = gp->ctx;
+  GpHostCopy* hc = host_copy(gp);
+  const size_t fs = (size_t)gp->Np * gp->Np;
+  double* par_s = gp->par + (size_t)s * kParStride;
+  const double diag0 = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 1];
+  // max_eps = ||src||_F of the matrix that failed
+  B7_CHECK(build_kxx(gp, s, 1));
+  double* rows = nullptr;
+  B7_CHECK(dev_alloc(&rows, (size_t)gp->N));
+  frob_rows_kernel<<<gp->N, 256, 0, ctx->stream>>>(gp->fac + s * fs, gp->Np, gp->N, rows);
+  b7_count(ctx);
+  std::vector<double> rh((size_t)gp->N);
+  B7_CUDA(cudaMemcpyAsync(rh.data(), rows, gp->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(rows);
+  double ss = 0.0;
+  for (double v : rh) ss += v;
+  const double max_eps = sqrt(ss);
+  double eps = 1e-8;
+  const double growth = 1.1;
+  while (true) {
+    if (eps > max_eps || !(max_eps == max_eps)) {
+      // chol(I): L = I, beta = r, logdet = 0
+      identity_kernel<<<(unsigned)((fs + 255) / 256), 256, 0, ctx->stream>>>(gp->fac + s * fs, gp->Np);
+      b7_count(ctx);
+      B7_CHECK(upload_residual(gp, s, hc->y));
+      B7_CHECK(factor(gp, s, 1));
+      gp->jitter[s] = INFINITY;
+      gp->info_host[s] = first_info;
+      return 0;
+    }
+    eps *= growth;
+    double d = diag0 + eps;
+    B7_CUDA(cudaMemcpyAsync(par_s + B7_MAX_DIMS + 1, &d, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));
+    B7_CHECK(build_kxx(gp, s, 1));
+    B7_CHECK(upload_residual(gp, s, hc->y));
+    B7_CHECK(factor(gp, s, 1));
+    int inf = 0;
+    B7_CUDA(cudaMemcpyAsync(&inf, gp->info + s, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (inf == 0) {
+      gp->jitter[s] = eps;
+      gp->info_host[s] = 0;
+      // leave the nominal diagonal in par (posterior uses sf2 only)
+      B7_CUDA(cudaMemcpyAsync(par_s + B7_MAX_DIMS + 1, &diag0, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      B7_CUDA(cudaStreamSynchronize(ctx->stream));
+      return 0;
+    }
+  }
+}
+
+static int gp_invert(b7_gp* gp, int s0, int count) {
+  b7_ctx* ctx = gp->ctx;
+  StageTimer t(ctx, ST_TRTRI);
+  int64_t before = ctx->launches;
+  B7_CHECK(b7_launch_trtri(gp, s0, count));
+  t.stop((int)(ctx->launches - before));
+  return 0;
+}
+
+int b7_gp_mark_ready(b7_gp* gp) {
+  if (!gp) return B7_ERR_ARG;
+  gp->ready = true;
+  gp->inverted = true;
+  return 0;
+}
+
+int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, int d, const double* hyp, int S,
+              int H, int noiseless, int flags, b7_gp** out, int* info, double* logml, double* jitter) {
+  if (!ctx || !out) { b7_set_error("gp_fit: null ctx/out"); return B7_ERR_ARG; }
+  *out = nullptr;
+  if (!X || !y || !hyp || N < 1 || d < 1 || d >= B7_MAX_DIMS || S < 1 || H != d + 3 ||
+      (kernel != B7_KERNEL_ARDSE && kernel != B7_KERNEL_MATERN52)) {
+    b7_set_error("gp_fit: bad arguments (N=%d d=%d S=%d H=%d kernel=%d; H must be d+3, d < 40)", N, d, S, H, kernel);
+    return B7_ERR_ARG;
+  }
+  B7_CUDA(cudaSetDevice(ctx->device));
+  b7_gp* gp = new b7_gp();
+  gp->ctx = ctx; gp->kernel = kernel; gp->N = N; gp->d = d; gp->S = S; gp->noiseless = noiseless;
+  gp->Np = (int)pad128(N); gp->NB = gp->Np / B7_NB;
+  gp->jitter.assign(S, 0.0); gp->info_host.assign(S, 0); gp->logml_host.assign(S, 0.0);
+  const size_t Np = gp->Np, fs = Np * Np, ds = (size_t)gp->NB * B7_NB * B7_NB;
+  int rc = 0;
+  auto fail = [&](int code) { b7_gp_free(gp); return code; };
+  if ((rc = dev_alloc(&gp->X, (size_t)N * d)) || (rc = dev_alloc(&gp->Xt, (size_t)d * Np)) || (rc = dev_alloc(&gp->y, (size_t)N)) ||
+      (rc = dev_alloc(&gp->par, (size_t)S * kParStride)) || (rc = dev_alloc(&gp->fac, (size_t)S * fs)) ||
+      (rc = dev_alloc(&gp->dinv, (size_t)S * ds)) || (rc = dev_alloc(&gp->dinvT, (size_t)S * ds)) ||
+      (rc = dev_alloc(&gp->beta, (size_t)S * Np)) || (rc = dev_alloc(&gp->tt, (size_t)S * B7_NB * Np)) ||
+      (rc = dev_alloc(&gp->logdet, (size_t)S)) || (rc = dev_alloc(&gp->info, (size_t)S)))
+    return fail(rc);
+  GpHostCopy* hc = new GpHostCopy();
+  hc->y.assign(y, y + N);
+  g_gp_host.push_back({gp, hc});
+  // parameters per draw (oracle/SPEC.md): w = exp(-log l), sf2 = exp(2 log sf), sn2 = exp(2 log sn)
+  gp->par_host.assign((size_t)S * kParStride, 0.0);
+  for (int s = 0; s < S; ++s) {
+    const double* h = hyp + (size_t)s * H;
+    double* p = gp->par_host.data() + (size_t)s * kParStride;
+    for (int i = 0; i < d; ++i) p[i] = exp(-h[i]);
+    const double sf2 = exp(2.0 * h[d]), sn2 = exp(2.0 * h[d + 1]);
+    p[B7_MAX_DIMS] = sf2;
+    p[B7_MAX_DIMS + 1] = sn2 + (noiseless ? 1e-8 * sf2 : 0.0);
+    p[B7_MAX_DIMS + 2] = h[d + 2];
+    p[B7_MAX_DIMS + 3] = sn2;
+  }
+  std::vector<double> xt((size_t)d * Np, 0.0), r((size_t)S * Np, 0.0);
+  for (int i = 0; i < N; ++i)
+    for (int k = 0; k < d; ++k) xt[(size_t)k * Np + i] = X[(size_t)i * d + k];
+  for (int s = 0; s < S; ++s) {
+    const double m = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 2];
+    for (int i = 0; i < N; ++i) r[(size_t)s * Np + i] = y[i] - m;
+  }
+  cudaStream_t st = ctx->stream;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(gp->X, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(gp->Xt, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(gp->y, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(gp->par, gp->par_host.data(), gp->par_host.size() * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(gp->beta, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+    b7_set_error("gp_fit upload: %s", cudaGetErrorString(e));
+    return fail(B7_ERR_CUDA);
+  }
+  if (flags == B7_FIT_DEFER) { *out = gp; return 0; }
+  if ((rc = b7_gp_fit_range(gp, 0, S, info, logml, jitter)) < 0) return fail(rc);
+  if (flags == B7_FIT_PREDICT) {
+    if ((rc = gp_invert(gp, 0, S)) < 0) return fail(rc);
+    gp->inverted = true;
+  }
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { b7_set_error("gp_fit: %s", cudaGetErrorString(e)); return fail(B7_ERR_CUDA); }
+  gp->ready = true;
+  *out = gp;
+  return 0;
+}
+
+int b7_gp_invert_range(b7_gp* gp, int s0, int count) {   // used with B7_FIT_DEFER
+  if (!gp || s0 < 0 || count < 0 || s0 + count > gp->S) return B7_ERR_ARG;
+  B7_CUDA(cudaSetDevice(gp->ctx->device));
+  B7_CHECK(gp_invert(gp, s0, count));
+  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  return 0;
+}
+
+int b7_gp_device_ptr(b7_gp* gp, int what, void** ptr, int64_t* bytes) {
+  if (!gp || !ptr) return B7_ERR_ARG;
+  const int64_t Np = gp->Np;
+  switch (what) {
+    case 0: *ptr = gp->fac; if (bytes) *bytes = (int64_t)gp->S * Np * Np * 8; return 0;
+    case 1: *ptr = gp->beta; if (bytes) *bytes = (int64_t)gp->S * Np * 8; return 0;
+    case 2: *ptr = gp->dinv; if (bytes) *bytes = (int64_t)gp->S * gp->NB * B7_NB * B7_NB * 8; return 0;
+    default: b7_set_error("gp_device_ptr: what=%d", what); return B7_ERR_ARG;
+  }
+}
+
+int b7_gp_read_factor(b7_gp* gp, int s, double* out_host) {
+  if (!gp || !out_host || s < 0 || s >= gp->S) return B7_ERR_ARG;
+  B7_CUDA(cudaSetDevice(gp->ctx->device));
+  B7_CUDA(cudaMemcpy2DAsync(out_host, (size_t)gp->N * 8, gp->fac + (size_t)s * gp->Np * gp->Np, (size_t)gp->Np * 8,
+                            (size_t)gp->N * 8, gp->N, cudaMemcpyDeviceToHost, gp->ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  return 0;
+}
+
+// posterior of draw s over `rows` device points (A: rows x d) -> mean/var device arrays (rows_pad long)
+static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, double* mean, double* var) {
+  b7_ctx* ctx = gp->ctx;
+  const int64_t rp = pad128(rows);
+  B7_CHECK(grow(&ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
+  {
+    StageTimer t(ctx, ST_KSTAR);
+    B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, A, rows, rp, gp->d, gp->Xt, gp->N, gp->Np,
+                                   gp->par + (size_t)s * kParStride, 0, ctx->ks, 0, 1, false));
+    t.stop(1);
+  }
+  {
+    StageTimer t(ctx, ST_POSTERIOR);
+    const double* p = gp->par_host.data() + (size_t)s * kParStride;
+    B7_CHECK(b7_launch_posterior(ctx, gp->fac + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
+                                 rp, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
+    t.stop(1);
+  }
+  return 0;
+}
+
+static int require_predict_state(b7_gp* gp) {
+  if (!gp->ready || !gp->inverted) {
+    b7_set_error("gp: factor not inverted (fit with B7_FIT_PREDICT, or b7_gp_invert_range + b7_gp_mark_ready)");
+    return B7_ERR_STATE;
+  }
+  return 0;
+}
+
+int b7_gp_predict(b7_gp* gp, int s, const double* Xs, int64_t M, double* mean, double* var) {
+  if (!gp || s < 0 || s >= gp->S || M < 0 || (M > 0 && (!Xs || !mean || !var))) { b7_set_error("gp_predict: bad arguments"); return B7_ERR_ARG; }
+  B7_CHECK(require_predict_state(gp));
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  const int64_t P = panel_rows(ctx);
+  B7_CHECK(grow(&ctx->xs_stage, &ctx->xs_bytes, (size_t)std::min(P, pad128(M)) * gp->d * 8));
+  B7_CHECK(grow(&ctx->moments, &ctx->moments_bytes, (size_t)2 * std::min(P, pad128(M)) * 8));
+  for (int64_t c0 = 0; c0 < M; c0 += P) {
+    const int64_t n = std::min(P, M - c0), np = pad128(n);
+    B7_CUDA(cudaMemcpyAsync(ctx->xs_stage, Xs + c0 * gp->d, (size_t)n * gp->d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* dm = ctx->moments; double* dv = ctx->moments + np;
+    B7_CHECK(posterior_panel(gp, s, ctx->xs_stage, n, dm, dv));
+    B7_CUDA(cudaMemcpyAsync(mean + c0, dm, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B7_CUDA(cudaMemcpyAsync(var + c0, dv, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ acquisition */
+
+struct PartBuf {
+  double* best = nullptr; int64_t* idx = nullptr; int64_t* nan = nullptr; int cap = 0;
+  ~PartBuf() { if (best) cudaFree(best); if (idx) cudaFree(idx); if (nan) cudaFree(nan); }
+};
+
+static int finish_argmax(b7_ctx* ctx, PartBuf& pb, int n_parts, double* best, int64_t* row0based, int64_t* nan_count) {
+  std::vector<double> hb((size_t)n_parts); std::vector<int64_t> hi((size_t)n_parts), hn((size_t)n_parts);
+  if (n_parts > 0) {
+    B7_CUDA(cudaMemcpyAsync(hb.data(), pb.best, n_parts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B7_CUDA(cudaMemcpyAsync(hi.data(), pb.idx, n_parts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B7_CUDA(cudaMemcpyAsync(hn.data(), pb.nan, n_parts * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  double bv = -INFINITY; int64_t bi = INT64_MAX, nn = 0;
+  for (int p = 0; p < n_parts; ++p) {
+    nn += hn[p];
+    if (hi[p] == INT64_MAX) continue;
+    if (hb[p] > bv || (hb[p] == bv && hi[p] < bi)) { bv = hb[p]; bi = hi[p]; }
+  }
+  if (bi == INT64_MAX) { *best = NAN; *row0based = -1; } else { *best = bv; *row0based = bi; }
+  *nan_count = nn;
+  return 0;
+}
+
+int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, int kind, double tradeoff, int bound,
+                       double sign, double fmin, double* score_host, int64_t* argmax_original, double* best,
+                       int64_t* nan_count) {
+  if (!gp || !grid || row0 < 0 || count < 0 || row0 + count > grid->rows || grid->d != gp->d ||
+      (kind != B7_SCORE_EI && kind != B7_SCORE_CB)) {
+    b7_set_error("acq_score: bad arguments (grid dims %d vs model dims %d)", grid ? grid->d : -1, gp ? gp->d : -1);
+    return B7_ERR_ARG;
+  }
+  B7_CHECK(require_predict_state(gp));
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  B7_CHECK(sync_removed(grid));
+  const int64_t P = panel_rows(ctx), Pp = std::min(P, pad128(std::max<int64_t>(count, 1)));
+  const int S = gp->S;
+  B7_CHECK(grow(&ctx->moments, &ctx->moments_bytes, (size_t)2 * S * Pp * 8));
+  const int64_t n_panels = (count + P - 1) / P;
+  PartBuf pb;
+  pb.cap = (int)(n_panels * b7_score_grid_size(ctx, P)) + 1;
+  B7_CHECK(dev_alloc(&pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.nan, (size_t)pb.cap));
+  double* score_dev = nullptr;
+  if (score_host) B7_CHECK(dev_alloc(&score_dev, (size_t)std::max<int64_t>(count, 1)));
+  int n_parts = 0, rc = 0;
+  for (int64_t c0 = 0; c0 < count && rc == 0; c0 += P) {
+    const int64_t n = std::min(P, count - c0), np = pad128(n);
+    double* dm = ctx->moments; double* dv = ctx->moments + (size_t)S * np;
+    for (int s = 0; s < S && rc == 0; ++s)
+      rc = posterior_panel(gp, s, grid->X + (row0 + c0) * grid->d, n, dm + (size_t)s * np, dv + (size_t)s * np);
+    if (rc < 0) break;
+    StageTimer t(ctx, ST_SCORE);
+    int parts = 0;
+    rc = b7_launch_score(ctx, kind, dm, dv, S, n, np, tradeoff, bound, sign, fmin, grid->removed_dev,
+                         (int64_t)grid->removed.size(), row0 + c0, score_dev ? score_dev + c0 : nullptr, pb.best + n_parts,
+                         pb.idx + n_parts, pb.nan + n_parts, &parts);
+    t.stop(1);
+    n_parts += parts;
+  }
+  double bv = NAN; int64_t r0 = -1, nn = 0;
+  if (rc == 0) rc = finish_argmax(ctx, pb, n_parts, &bv, &r0, &nn);
+  if (rc == 0 && score_host && count > 0) {
+    cudaError_t e = cudaMemcpyAsync(score_host, score_dev, (size_t)count * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { b7_set_error("acq_score D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
+  }
+  if (score_dev) cudaFree(score_dev);
+  if (rc < 0) return rc;
+  if (argmax_original) *argmax_original = r0 + 1;
+  if (best) *best = bv;
+  if (nan_count) *nan_count = nn;
+  return 0;
+}
+
+int b7_acq_score(b7_gp* gp, b7_grid* grid, int kind, double tradeoff, int bound, double sign, double fmin,
+                 double* score_host, int64_t* argmax, int64_t* argmax_original, double* best, int64_t* nan_count) {
+  if (!grid) { b7_set_error("acq_score: null grid"); return B7_ERR_ARG; }
+  int64_t orig = 0;
+  B7_CHECK(b7_acq_score_range(gp, grid, 0, grid->rows, kind, tradeoff, bound, sign, fmin, score_host, &orig, best, nan_count));
+  if (argmax_original) *argmax_original = orig;
+  if (argmax) {
+    if (orig <= 0) *argmax = 0;
+    else {
+      int64_t r = orig - 1;
+      int64_t below = std::lower_bound(grid->removed.begin(), grid->removed.end(), r) - grid->removed.begin();
+      *argmax = r - below + 1;
+    }
+  }
+  return 0;
+}
+
+int b7_score_moments(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, double tradeoff,
+                     int bound, double sign, double fmin, double* score_host, int64_t* argmax, double* best,
+                     int64_t* nan_count) {
+  if (!ctx || S < 1 || M < 0 || (M > 0 && (!mean || !var)) || (kind != B7_SCORE_EI && kind != B7_SCORE_CB)) { b7_set_error("score_moments: bad arguments"); return B7_ERR_ARG; }
+  B7_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)S * std::max<int64_t>(M, 1);
+  double *dm = nullptr, *dv = nullptr, *ds = nullptr;
+  B7_CHECK(dev_alloc(&dm, n)); B7_CHECK(dev_alloc(&dv, n)); B7_CHECK(dev_alloc(&ds, (size_t)std::max<int64_t>(M, 1)));
+  PartBuf pb; pb.cap = b7_score_grid_size(ctx, M) + 1;
+  B7_CHECK(dev_alloc(&pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.nan, (size_t)pb.cap));
+  int rc = 0, parts = 0;
+  if (M > 0) {
+    B7_CUDA(cudaMemcpyAsync(dm, mean, (size_t)S * M * 8, cudaMemcpyHostToDevice, ctx->stream));
+    B7_CUDA(cudaMemcpyAsync(dv, var, (size_t)S * M * 8, cudaMemcpyHostToDevice, ctx->stream));
+    StageTimer t(ctx, ST_SCORE);
+    rc = b7_launch_score(ctx, kind, dm, dv, S, M, M, tradeoff, bound, sign, fmin, nullptr, 0, 0, ds, pb.best, pb.idx, pb.nan, &parts);
+    t.stop(1);
+  }
+  double bv = NAN; int64_t r0 = -1, nn = 0;
+  if (rc == 0) rc = finish_argmax(ctx, pb, parts, &bv, &r0, &nn);
+  if (rc == 0 && score_host && M > 0) {
+    cudaError_t e = cudaMemcpyAsync(score_host, ds, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { b7_set_error("score_moments D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
+  }
+  cudaFree(dm); cudaFree(dv); cudaFree(ds);
+  if (rc < 0) return rc;
+  if (argmax) *argmax = r0 + 1;
+  if (best) *best = bv;
+  if (nan_count) *nan_count = nn;
+  return 0;
+}
+
+}  // extern "C"

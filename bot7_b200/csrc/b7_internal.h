@@ -1,0 +1,130 @@
+// Internal declarations shared by the translation units of libbot7_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bot7_b200.h"
+
+#define B7_NB 128            // Cholesky / TRMM block size == GEMM tile edge
+#define B7_MAX_DIMS 40       // grids/sobol.lua:31
+#define B7_SOBOL_BITS 30     // grids/sobol.lua:32
+
+void b7_set_error(const char* fmt, ...);
+
+#define B7_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      b7_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #expr); \
+      return B7_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define B7_CHECK(expr)                 \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ < 0) return rc_;           \
+  } while (0)
+
+enum { ST_SOBOL = 0, ST_KBUILD, ST_POTRF, ST_TRTRI, ST_KSTAR, ST_POSTERIOR, ST_SCORE, ST_BLR, ST_COUNT };
+
+struct b7_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double stage_ms[ST_COUNT] = {0};
+  int64_t stage_calls[ST_COUNT] = {0};
+  bool profiling = false;
+  int64_t launches = 0;
+  // scratch for the posterior pass (grown on demand)
+  double* ks = nullptr;        // K* panel, [panel_rows][Np]
+  size_t ks_bytes = 0;
+  double* moments = nullptr;   // [2][S][panel_rows] mean, var
+  size_t moments_bytes = 0;
+  double* xs_stage = nullptr;  // device staging of host candidate points
+  size_t xs_bytes = 0;
+};
+
+struct b7_grid {
+  b7_ctx* ctx = nullptr;
+  int64_t rows = 0;   // original rows
+  int d = 0;
+  double* X = nullptr;            // device, rows x d row-major
+  std::vector<int64_t> removed;   // sorted original 0-based rows (tombstones)
+  int64_t* removed_dev = nullptr; // device copy (capacity grows)
+  int64_t removed_cap = 0;
+  bool removed_dirty = false;
+};
+
+struct b7_gp {
+  b7_ctx* ctx = nullptr;
+  int kernel = 0, N = 0, d = 0, S = 0, Np = 0, NB = 0, DT = 8, noiseless = 0;
+  bool inverted = false, ready = false;
+  double* X = nullptr;      // device N x d
+  double* Xt = nullptr;     // device DT... x Np transposed, zero padded ([d][Np])
+  double* y = nullptr;      // device N
+  double* par = nullptr;    // device S x (B7_MAX_DIMS + 4): w[0..39], sf2, diag_add, m, sn2
+  std::vector<double> par_host;
+  double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1 (row-major, lower)
+  double* dinv = nullptr;   // device S x NB x 128 x 128 : inverse of the diagonal blocks of L
+  double* dinvT = nullptr;  // device, transposes of dinv
+  double* beta = nullptr;   // device S x Np : r -> L^-1 (y - m)
+  double* tt = nullptr;     // device S x 128 x Np : scratch of the inversion sweep
+  double* logdet = nullptr; // device S : sum log L_ii
+  int* info = nullptr;      // device S
+  std::vector<double> jitter;
+  std::vector<int> info_host;
+  std::vector<double> logml_host;
+};
+
+struct b7_blr {
+  b7_ctx* ctx = nullptr;
+  int N = 0, D = 0, S = 0;
+  double* Linv = nullptr;  // device S x D x D : L_A^-1 (lower)
+  double* w = nullptr;     // device S x D
+  double* par = nullptr;   // device S x 4: alpha_p, beta, m, 1/beta
+  std::vector<double> par_host;
+};
+
+// ---- launch bookkeeping ----
+static inline void b7_count(b7_ctx* ctx, int n = 1) { ctx->launches += n; }
+// Brackets the launches of one stage with CUDA events on the context stream (only when profiling
+// is on: it synchronises).  n = number of kernel launches of the stage inside the bracket.
+struct StageTimer {
+  b7_ctx* ctx; int stage;
+  StageTimer(b7_ctx* c, int s) : ctx(c), stage(s) { if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream); }
+  void stop(int n = 1) {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stage_ms[stage] += ms;
+    ctx->stage_calls[stage] += n;
+  }
+};
+
+// ---- kernels' host launchers (defined in the .cu files) ----
+// sobol.cu
+void b7_sobol_directions_host(int dims, uint32_t* out /* dims*30 */);
+int b7_launch_sobol(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, const double* mins_dev,
+                    const double* maxes_dev, double* out_dev);
+// cov.cu
+int b7_launch_cov_batched(b7_ctx* ctx, int kernel, const double* A /* rows x d */, int64_t rows, int64_t rows_pad, int d,
+                          const double* Xt /* [d][Np] */, int N, int Np, const double* par, int64_t par_stride,
+                          double* out /* rows_pad x Np */, int64_t out_stride, int batch, bool is_kxx);
+// potrf.cu
+int b7_launch_potrf(b7_gp* gp, int s0, int count);      // K -> L, beta, logdet, info for draws [s0,s0+count)
+int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
+// posterior.cu
+int b7_launch_posterior(b7_ctx* ctx, const double* Linv, const double* beta, int Np, const double* ks,
+                        int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
+// score.cu
+int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,
+                    double tradeoff, int bound, double sign, double fmin, const int64_t* removed, int64_t n_removed,
+                    int64_t row_base, double* score_out /* nullable, M */, double* part_best, int64_t* part_idx,
+                    int64_t* part_nan, int* n_parts);
+int b7_argmax_finish(b7_ctx* ctx, const double* part_best, const int64_t* part_idx, const int64_t* part_nan,
+                     int n_parts, double* best, int64_t* idx0, int64_t* nan_count);

@@ -1,0 +1,110 @@
+// FP64 tensor-core tile engine shared by the Cholesky, the triangular inversion and the posterior
+// pass:  acc(128x128) += A(128 x K) * B(128 x K)^T, both operands row-major with k contiguous.
+//
+// sm_100a has no tcgen05 kind for f64 and wgmma does not exist; the FP64 tensor path is warp-level
+// mma.sync.m8n8k4.f64, which ptxas lowers to DMMA.8x8x4 (one per 16 clk per SM sub-partition;
+// measured 37.1 TFLOP/s on B200, tools/fp64_peak.cu).  A CTA of 8 warps owns a 128x128 tile, a warp
+// a 64x32 sub-tile = 8x4 DMMA fragments (128 accumulator registers per thread).
+//
+// Shared-memory layout ("fragment order"): a 128 x 16 operand k-tile is stored as
+// [k-group g = 0..3][row 0..127][4 doubles]; the A/B fragment of rows 8f..8f+7, k-group g is then the
+// 256 contiguous bytes at g*4096 + f*256, read by one conflict-free LDS.64 per lane.  cp.async
+// moves 16-byte pieces from the row-major global tile into that order (two lanes per row, 512
+// contiguous shared bytes per warp instruction), 4-stage pipeline, one __syncthreads per k-tile.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b7g {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
+constexpr int OPERAND_DOUBLES = BM * BK;              // 2048 doubles = 16 KB
+constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;    // A then B
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 128 KB
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// One 128 x 16 k-tile of a k-contiguous operand: g points at (row 0, k0), ld in doubles.
+__device__ __forceinline__ void load_operand(double* s, const double* __restrict__ g, long long ld, int tid) {
+  const int row = tid >> 1, h = tid & 1;
+  const double* src = g + (long long)row * ld + h * 2;
+  double* dst = s + row * 4 + h * 2;
+#pragma unroll
+  for (int g4 = 0; g4 < 4; ++g4) cp_async16(dst + g4 * (BM * 4), src + g4 * 4);
+}
+
+struct Acc {
+  double c[8][4][2];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  }
+};
+
+// multiply-accumulate one staged k-tile: warp (wm, wn) owns rows 64*wm.., cols 32*wn..
+__device__ __forceinline__ void compute_stage(const double* __restrict__ sA, const double* __restrict__ sB, int wm,
+                                              int wn, int lane, Acc& acc) {
+#pragma unroll
+  for (int g4 = 0; g4 < 4; ++g4) {
+    double a[8], b[4];
+    const double* pa = sA + g4 * (BM * 4) + (64 * wm) * 4 + lane;
+    const double* pb = sB + g4 * (BN * 4) + (32 * wn) * 4 + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = pa[i * 32];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = pb[j * 32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc.c[i][j][0], acc.c[i][j][1], a[i], b[j]);
+  }
+}
+
+// acc += A[0:128, 0:16*KT] * B[0:128, 0:16*KT]^T  (gA, gB point at the first k column)
+__device__ __forceinline__ void mainloop(const double* __restrict__ gA, long long lda, const double* __restrict__ gB,
+                                         long long ldb, int KT, double* smem, Acc& acc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) {
+      load_operand(smem + s * STAGE_DOUBLES, gA + s * BK, lda, tid);
+      load_operand(smem + s * STAGE_DOUBLES + OPERAND_DOUBLES, gB + s * BK, ldb, tid);
+    }
+    cp_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < KT) {
+      double* st = smem + (nxt % STAGES) * STAGE_DOUBLES;
+      load_operand(st, gA + (long long)nxt * BK, lda, tid);
+      load_operand(st + OPERAND_DOUBLES, gB + (long long)nxt * BK, ldb, tid);
+    }
+    cp_commit();
+    const double* st = smem + (kt % STAGES) * STAGE_DOUBLES;
+    compute_stage(st, st + OPERAND_DOUBLES, wm, wn, lane, acc);
+  }
+  cp_wait<0>();
+  __syncthreads();   // smem may be reused by the caller's epilogue
+}
+
+// coordinates of accumulator fragment (i, j) of this lane inside the 128x128 tile
+__device__ __forceinline__ int frag_row(int wm, int i, int lane) { return 64 * wm + 8 * i + (lane >> 2); }
+__device__ __forceinline__ int frag_col(int wn, int j, int lane) { return 32 * wn + 8 * j + 2 * (lane & 3); }
+
+}  // namespace b7g
