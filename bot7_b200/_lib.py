@@ -37,6 +37,8 @@ SIGNATURES = {
     "b7_set_profiling": (_i, [_p, _i]),
     "b7_reset_stage_timers": (_i, [_p]),
     "b7_last_stage_ms": (_i, [_p, _i, _dp, _lp]),
+    "b7_timer_begin": (_i, [_p]),
+    "b7_timer_end": (_i, [_p, _dp]),
     "b7_launch_count": (_l, [_p]),
     "b7_sobol_directions": (_i, [_i, C.POINTER(C.c_uint32)]),
     "b7_sobol_generate": (_i, [_p, _i, _l, _l, _dp, _dp, _dp, C.POINTER(_p)]),
@@ -153,6 +155,14 @@ class Context:
             check(lib().b7_last_stage_ms(self.handle, k, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+    def timer_begin(self):
+        check(lib().b7_timer_begin(self.handle), "b7_timer_begin")
+
+    def timer_end(self) -> float:
+        ms = _d(0.0)
+        check(lib().b7_timer_end(self.handle, C.byref(ms)), "b7_timer_end")
+        return ms.value
 
     def launch_count(self) -> int:
         return int(lib().b7_launch_count(self.handle))

@@ -156,6 +156,8 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
+  B7_CUDA(cudaEventCreate(&ctx->tm0));
+  B7_CUDA(cudaEventCreate(&ctx->tm1));
   *out = ctx;
   return 0;
 }
@@ -169,6 +171,8 @@ void b7_shutdown(b7_ctx* ctx) {
   if (ctx->xs_stage) cudaFree(ctx->xs_stage);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->tm0);
+  cudaEventDestroy(ctx->tm1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -176,6 +180,23 @@ void b7_shutdown(b7_ctx* ctx) {
 int b7_sync(b7_ctx* ctx) {
   if (!ctx) return B7_ERR_ARG;
   B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b7_timer_begin(b7_ctx* ctx) {
+  if (!ctx) return B7_ERR_ARG;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  B7_CUDA(cudaEventRecord(ctx->tm0, ctx->stream));
+  return 0;
+}
+int b7_timer_end(b7_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return B7_ERR_ARG;
+  B7_CUDA(cudaEventRecord(ctx->tm1, ctx->stream));
+  B7_CUDA(cudaEventSynchronize(ctx->tm1));
+  float f = 0;
+  B7_CUDA(cudaEventElapsedTime(&f, ctx->tm0, ctx->tm1));
+  *ms = f;
   return 0;
 }
 

@@ -34,7 +34,7 @@ struct b7_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   double stage_ms[ST_COUNT] = {0};
   int64_t stage_calls[ST_COUNT] = {0};
   bool profiling = false;

@@ -8,13 +8,15 @@
 //
 // Right-looking, block size 128 (= the DMMA tile edge of gemm_tile.cuh), row-major lower storage,
 // matrices padded to a multiple of 128 with identity.  Per block column j:
-//   diag  : one CTA per draw factors the 128x128 diagonal block in shared memory and, fused in the
-//           same sweep, inverts it (Gauss-Jordan on the lower triangle; the inverse lives in the
-//           upper triangle of the same shared array); it also produces x_j = L_jj^-1 r_j, the running
-//           log-determinant and info.
+//   diag  : one CTA per draw factors the 128x128 diagonal block with the rows held in registers and
+//           then inverts it (Gauss-Jordan forward elimination); it also produces x_j = L_jj^-1 r_j,
+//           the running log-determinant and info.
 //   panel : L21 = A21 * inv(L11)^T as DMMA tiles; the epilogue folds r_i -= L21 x_j, so the forward
 //           substitution for beta costs no extra pass over L.
-//   trail : A22 -= L21 L21^T on the lower tiles (DMMA).
+//   trail : A22 -= L21 L21^T on the lower tiles (DMMA).  Two-level blocking: inside an outer panel of
+//           4 blocks only the panel's own columns are updated per step (k = 128); the tiles to the
+//           right of the panel are updated once per outer panel with k = 512, so most flops run in
+//           long-k launches with a quarter of the read-modify-write traffic on C.
 // Inversion (LAPACK dtrtri order, in place, column sweep from the right):
 //   T = L[j+1:, j] * inv(L_jj)  (stored transposed), then  X[j+1:, j] = -Linv[j+1:, j+1:] * T.
 #include "b7_internal.h"
@@ -25,77 +27,155 @@ using namespace b7g;
 namespace {
 
 constexpr int NBK = B7_NB;          // 128
-constexpr int DLD = NBK + 1;        // leading dimension of the diag workspace (129 doubles)
 constexpr int DIAG_THREADS = 512;
-constexpr int DIAG_SMEM = NBK * DLD * 8 + NBK * 8;
+// shared: Lcol[128][128] | pivs[128] | invs[128] | rowbuf[2][128] | rj[128] | xpart[4][128] | lg[128]
+constexpr int DIAG_SMEM = (NBK * NBK + 11 * NBK) * 8;
 
 // ---- diagonal block: potf2 + inverse + x_j + logdet + info -------------------------------------
-__global__ void __launch_bounds__(DIAG_THREADS)
+// Thread (r, part) keeps 32 entries of row r in registers (static indexing: the column loop is
+// unrolled in chunks of 32), so a step is one shared-memory column broadcast, one barrier and
+// 32 predicated DFMAs -- no read-modify-write chains through shared memory.  Two sweeps: the
+// right-looking Cholesky, then Gauss-Jordan forward elimination for the inverse.
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, double* __restrict__ dinv,
             double* __restrict__ dinvT, long long dinv_stride, double* __restrict__ beta, double* __restrict__ logdet,
             int* __restrict__ info, int s0) {
   extern __shared__ double sm[];
-  double* a = sm;                   // a[i*DLD + k]: k<=i lower of A/L ; k>i: W/X[k-1][i] (inverse, transposed)
-  double* xr = sm + NBK * DLD;      // r_j, then x_j
+  double* Lcol = sm;                       // Lcol[q*128 + r] = A[r][q] as it was when column q was eliminated
+  double* pivs = sm + NBK * NBK;
+  double* invs = pivs + NBK;
+  double* rowbuf = invs + NBK;             // [2][128]
+  double* rj = rowbuf + 2 * NBK;
+  double* xpart = rj + NBK;                // [4][128]
+  double* lg = xpart + 4 * NBK;
   const int s = s0 + blockIdx.x, tid = threadIdx.x;
+  const int r = tid & 127, part = tid >> 7, c0 = part * 32;
   double* blk = fac + (long long)s * fac_stride + (long long)j * NBK * Np + (long long)j * NBK;
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    int i = e >> 7, k = e & 127;
-    double v = blk[(long long)i * Np + k];
-    if (k <= i) a[i * DLD + k] = v;
-    if (k > i) a[i * DLD + k + 1] = 0.0;     // W[k][i] = 0 for i < k
-    if (k == i) a[i * DLD + i + 1] = 1.0;    // W[i][i] = 1
+  double a[32];
+  {
+    const double2* src = reinterpret_cast<const double2*>(blk + (long long)r * Np + c0);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double2 v = src[kk];
+      a[2 * kk] = v.x;
+      a[2 * kk + 1] = v.y;
+    }
   }
-  if (tid < NBK) xr[tid] = beta[(long long)s * Np + j * NBK + tid];
-  double ld_acc = 0.0;
+  if (tid < NBK) rj[tid] = beta[(long long)s * Np + j * NBK + tid];
   int my_info = 0;
-  __syncthreads();
-  for (int q = 0; q < NBK; ++q) {
-    const double piv = a[q * DLD + q];
-    const double lq = sqrt(piv);
-    const double inv = 1.0 / lq;
-    if (tid == 0) {
-      if (!(piv > 0.0) && my_info == 0) my_info = j * NBK + q + 1;
-      ld_acc += log(lq);
+  // ---- sweep 1: Cholesky ----
+  for (int pq = 0; pq < 4; ++pq) {
+#pragma unroll
+    for (int qq = 0; qq < 32; ++qq) {
+      const int q = pq * 32 + qq;
+      if (part == pq) Lcol[q * NBK + r] = a[qq];
+      __syncthreads();
+      const double piv = Lcol[q * NBK + q];
+      const double inv = rsqrt(piv);
+      if (tid == 0) {
+        pivs[q] = piv;
+        invs[q] = inv;
+        if (!(piv > 0.0) && my_info == 0) my_info = j * NBK + q + 1;
+      }
+      const double arq = Lcol[q * NBK + r];
+      if (c0 + 31 > q) {   // warp-uniform: this 32-column slice still has columns right of q
+        const double t = arq * (inv * inv);   // A_rq / pivot
+        const double2* colv = reinterpret_cast<const double2*>(Lcol + q * NBK + c0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double2 cv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cv[u] = colv[h * 8 + u];   // broadcast loads, issued together
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int kk = h * 16 + 2 * u, k = c0 + kk;
+            const double n0 = fma(-t, cv[u].x, a[kk]), n1 = fma(-t, cv[u].y, a[kk + 1]);
+            a[kk] = (k > q && k <= r) ? n0 : a[kk];
+            a[kk + 1] = (k + 1 > q && k + 1 <= r) ? n1 : a[kk + 1];
+          }
+        }
+      }
+      if (part == pq) {
+        if (r > q) a[qq] = arq * inv;
+        else if (r == q) a[qq] = piv * inv;
+      }
     }
-    __syncthreads();
-    // scale column q of L (rows > q) and row q of the inverse (cols <= q)
-    if (tid < NBK) {
-      if (tid > q) a[tid * DLD + q] *= inv;
-      else a[tid * DLD + q + 1] *= inv;      // X[q][tid] = W[q][tid] / l_qq
-      if (tid == q) a[q * DLD + q] = lq;
-    }
-    __syncthreads();
-    // rows i > q: trailing update (k' > q) and inverse update (k' <= q)
-    const int n_rows = NBK - 1 - q;
-    for (int e = tid; e < n_rows * NBK; e += DIAG_THREADS) {
-      const int i = q + 1 + (e >> 7), kk = e & 127;
-      if (kk > i) continue;
-      const double liq = a[i * DLD + q];
-      if (kk > q) a[i * DLD + kk] -= liq * a[kk * DLD + q];
-      else a[kk * DLD + i + 1] -= liq * a[kk * DLD + q + 1];
-    }
-    __syncthreads();
   }
-  // x_j = inv(L_jj) r_j
-  double xv = 0.0;
-  if (tid < NBK) {
-    for (int c = 0; c <= tid; ++c) xv += a[c * DLD + tid + 1] * xr[c];
+  // L block back to global (upper part zeroed)
+  {
+    double2* dst = reinterpret_cast<double2*>(blk + (long long)r * Np + c0);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = c0 + 2 * kk;
+      dst[kk] = make_double2(k <= r ? a[2 * kk] : 0.0, k + 1 <= r ? a[2 * kk + 1] : 0.0);
+    }
+  }
+  __syncthreads();   // invs complete
+  // ---- sweep 2: inverse by forward elimination, W starts as the identity ----
+  double w[32];
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) w[kk] = (c0 + kk == r) ? 1.0 : 0.0;
+  for (int pq = 0; pq < 4; ++pq) {
+#pragma unroll
+    for (int qq = 0; qq < 32; ++qq) {
+      const int q = pq * 32 + qq;
+      const double inv = invs[q];
+      double* buf = rowbuf + (q & 1) * NBK;
+      if (r == q) {
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          w[kk] *= inv;            // X[q][c] = W[q][c] / l_qq
+          buf[c0 + kk] = w[kk];
+        }
+      }
+      __syncthreads();
+      if (c0 <= q) {   // warp-uniform: this slice has columns <= q
+        const double liq = Lcol[q * NBK + r] * inv;   // L[r][q]
+        const double2* rowv = reinterpret_cast<const double2*>(buf + c0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double2 rv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rv[u] = rowv[h * 8 + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int kk = h * 16 + 2 * u, c = c0 + kk;
+            const double n0 = fma(-liq, rv[u].x, w[kk]), n1 = fma(-liq, rv[u].y, w[kk + 1]);
+            w[kk] = (r > q && c <= q) ? n0 : w[kk];
+            w[kk + 1] = (r > q && c + 1 <= q) ? n1 : w[kk + 1];
+          }
+        }
+      }
+    }
+  }
+  // x_j = inv(L_jj) r_j ; outputs
+  double xp = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk)
+    if (c0 + kk <= r) xp = fma(w[kk], rj[c0 + kk], xp);
+  xpart[part * NBK + r] = xp;
+  if (tid < NBK) lg[tid] = log(pivs[tid] * invs[tid]);
+  double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  {
+    double2* dst = reinterpret_cast<double2*>(di + r * NBK + c0);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = c0 + 2 * kk;
+      dst[kk] = make_double2(k <= r ? w[2 * kk] : 0.0, k + 1 <= r ? w[2 * kk + 1] : 0.0);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) dt[(c0 + kk) * NBK + r] = (c0 + kk <= r) ? w[kk] : 0.0;
   }
   __syncthreads();
-  if (tid < NBK) beta[(long long)s * Np + j * NBK + tid] = xv;
+  if (tid < NBK)
+    beta[(long long)s * Np + j * NBK + tid] = ((xpart[tid] + xpart[NBK + tid]) + xpart[2 * NBK + tid]) + xpart[3 * NBK + tid];
   if (tid == 0) {
+    double ld_acc = 0.0;
+    for (int q = 0; q < NBK; ++q) ld_acc += lg[q];
     logdet[s] = (j == 0 ? 0.0 : logdet[s]) + ld_acc;
     if (j == 0) info[s] = my_info;
     else if (info[s] == 0 && my_info != 0) info[s] = my_info;
-  }
-  double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    int i = e >> 7, k = e & 127;
-    blk[(long long)i * Np + k] = (k <= i) ? a[i * DLD + k] : 0.0;
-    di[e] = (k <= i) ? a[k * DLD + i + 1] : 0.0;   // X[i][k]
-    dt[e] = (k >= i) ? a[i * DLD + k + 1] : 0.0;   // X[k][i]
   }
 }
 
@@ -133,19 +213,22 @@ panel_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, cons
   }
 }
 
-// ---- trailing update: A22 -= L21 L21^T (lower tiles) ---------------------------------------------
+// ---- trailing update: C[it][nt] -= L[it][kb0:kb1] L[nt][kb0:kb1]^T on lower tiles ---------------
+// it = it0 + blockIdx.x, nt = nt0 + blockIdx.y (tiles above the diagonal exit at once).  Used with
+// one k block inside the current outer panel and with the whole outer panel (k = 128 * W) for the
+// tiles to its right: the long-k launches carry most of the flops with one read-modify-write of C.
 __global__ void __launch_bounds__(THREADS, 1)
-trail_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, int s0) {
+trail_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, int kb1, int it0, int nt0, int s0) {
   extern __shared__ __align__(16) double smem[];
-  const int it = j + 1 + blockIdx.x, nt = j + 1 + blockIdx.y;
+  const int it = it0 + blockIdx.x, nt = nt0 + blockIdx.y;
   if (nt > it) return;
   const int s = s0 + blockIdx.z;
   double* base = fac + (long long)s * fac_stride;
-  const double* A = base + (long long)it * NBK * Np + (long long)j * NBK;
-  const double* B = base + (long long)nt * NBK * Np + (long long)j * NBK;
+  const double* A = base + (long long)it * NBK * Np + (long long)kb0 * NBK;
+  const double* B = base + (long long)nt * NBK * Np + (long long)kb0 * NBK;
   double* C = base + (long long)it * NBK * Np + (long long)nt * NBK;
   Acc acc; acc.zero();
-  mainloop(A, Np, B, Np, NBK / BK, smem, acc);
+  mainloop(A, Np, B, Np, (kb1 - kb0) * (NBK / BK), smem, acc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -233,15 +316,27 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   B7_CHECK(set_attrs());
   const int Np = gp->Np, NB = gp->NB;
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK;
-  for (int j = 0; j < NB; ++j) {
-    diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, gp->dinvT, ds, gp->beta,
-                                                                gp->logdet, gp->info, s0);
-    b7_count(ctx);
-    const int rem = NB - 1 - j;
-    if (rem > 0) {
-      panel_kernel<<<dim3(rem, 1, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
-      trail_kernel<<<dim3(rem, rem, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, s0);
-      b7_count(ctx, 2);
+  const int W = 4;   // outer panel = 4 blocks (512 columns)
+  for (int J = 0; J < NB; J += W) {
+    const int Jend = J + W < NB ? J + W : NB;
+    for (int j = J; j < Jend; ++j) {
+      diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, gp->dinvT, ds, gp->beta,
+                                                                  gp->logdet, gp->info, s0);
+      b7_count(ctx);
+      const int rem = NB - 1 - j;
+      if (rem > 0) {
+        panel_kernel<<<dim3(rem, 1, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
+        b7_count(ctx);
+      }
+      if (Jend - 1 - j > 0) {   // columns j+1 .. Jend-1 of the outer panel, all rows below
+        trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
+        b7_count(ctx);
+      }
+    }
+    const int right = NB - Jend;
+    if (right > 0) {
+      trail_kernel<<<dim3(right, right, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
+      b7_count(ctx);
     }
   }
   B7_CUDA(cudaGetLastError());

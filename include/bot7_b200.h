@@ -46,6 +46,9 @@ int  b7_sync(b7_ctx* ctx);
 int  b7_set_profiling(b7_ctx* ctx, int on);   /* off by default: stage timing synchronises per launch */
 int  b7_reset_stage_timers(b7_ctx* ctx);
 int  b7_last_stage_ms(b7_ctx* ctx, int stage, double* ms_total, int64_t* launches);
+/* device-side stopwatch: CUDA events recorded on the context stream (begin; ...calls...; end -> ms) */
+int  b7_timer_begin(b7_ctx* ctx);
+int  b7_timer_end(b7_ctx* ctx, double* ms);
 /* number of kernels this library has launched on the context since b7_init */
 int64_t b7_launch_count(b7_ctx* ctx);
 
