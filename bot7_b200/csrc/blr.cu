@@ -269,6 +269,11 @@ int b7_blr_fit(b7_ctx* ctx, const double* Z0, const double* y, int N, int D, con
   cudaMemcpyAsync(dZ, Z0, (size_t)N * D * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(blr->par, blr->par_host.data(), (size_t)S * 4 * 8, cudaMemcpyHostToDevice, st);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(blr_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kMaxD * (kMaxD + 1) + 2 * kMaxD) * 8);
+    attr_done = true;
+  }
   StageTimer t(ctx, ST_BLR);
   gram_kernel<<<blocks, 256, (32 * (D + 1) + 32) * 8, st>>>(dZ, dy, N, D, partial);
   blr_finish_kernel<<<S, 256, (2 * D * (D + 1) + 2 * D) * 8, st>>>(partial, blocks, D, blr->par, blr->Linv, blr->w, dinfo);
