@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbot7_b200.so")
+LIB_PATH = os.environ.get("BOT7_B200_LIB") or os.path.join(_HERE, "libbot7_b200.so")
 
 KERNEL_ARDSE, KERNEL_MATERN52 = 0, 1
 SCORE_EI, SCORE_CB = 0, 1

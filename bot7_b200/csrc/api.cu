@@ -327,7 +327,7 @@ void b7_gp_free(b7_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
-  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facT, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (size_t i = 0; i < g_gp_host.size(); ++i)
     if (g_gp_host[i].first == gp) { delete g_gp_host[i].second; g_gp_host.erase(g_gp_host.begin() + i); break; }
@@ -432,12 +432,22 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
   B7_CHECK(b7_launch_trtri(gp, s0, count));
+  // tiled copy of L^-1 for the posterior pass (allocated on first use: logml-only fits never need it)
+  const size_t fs = (size_t)gp->Np * gp->Np;
+  if (!gp->facT) B7_CHECK(dev_alloc(&gp->facT, (size_t)gp->S * fs));
+  B7_CHECK(b7_launch_retile(ctx, gp->fac + (size_t)s0 * fs, gp->facT + (size_t)s0 * fs, gp->Np, count));
   t.stop((int)(ctx->launches - before));
   return 0;
 }
 
 int b7_gp_mark_ready(b7_gp* gp) {
   if (!gp) return B7_ERR_ARG;
+  // slots filled by the host (all-gather into fac): refresh the tiled copy of every draw
+  B7_CUDA(cudaSetDevice(gp->ctx->device));
+  const size_t fs = (size_t)gp->Np * gp->Np;
+  if (!gp->facT) B7_CHECK(dev_alloc(&gp->facT, (size_t)gp->S * fs));
+  B7_CHECK(b7_launch_retile(gp->ctx, gp->fac, gp->facT, gp->Np, gp->S));
+  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
   gp->ready = true;
   gp->inverted = true;
   return 0;
@@ -547,13 +557,13 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   {
     StageTimer t(ctx, ST_KSTAR);
     B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, A, rows, rp, gp->d, gp->Xt, gp->N, gp->Np,
-                                   gp->par + (size_t)s * kParStride, 0, ctx->ks, 0, 1, false));
+                                   gp->par + (size_t)s * kParStride, 0, ctx->ks, 0, 1, false, true));
     t.stop(1);
   }
   {
     StageTimer t(ctx, ST_POSTERIOR);
     const double* p = gp->par_host.data() + (size_t)s * kParStride;
-    B7_CHECK(b7_launch_posterior(ctx, gp->fac + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
+    B7_CHECK(b7_launch_posterior(ctx, gp->facT + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
                                  rp, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
     t.stop(1);
   }

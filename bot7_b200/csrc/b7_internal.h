@@ -69,6 +69,7 @@ struct b7_gp {
   double* par = nullptr;    // device S x (B7_MAX_DIMS + 4): w[0..39], sf2, diag_add, m, sn2
   std::vector<double> par_host;
   double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1 (row-major, lower)
+  double* facT = nullptr;   // device S x Np x Np : L^-1 in the tiled (fragment-order) layout read by the posterior pass
   double* dinv = nullptr;   // device S x NB x 128 x 128 : inverse of the diagonal blocks of L
   double* dinvT = nullptr;  // device, transposes of dinv
   double* beta = nullptr;   // device S x Np : r -> L^-1 (y - m)
@@ -114,12 +115,13 @@ int b7_launch_sobol(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, co
 // cov.cu
 int b7_launch_cov_batched(b7_ctx* ctx, int kernel, const double* A /* rows x d */, int64_t rows, int64_t rows_pad, int d,
                           const double* Xt /* [d][Np] */, int N, int Np, const double* par, int64_t par_stride,
-                          double* out /* rows_pad x Np */, int64_t out_stride, int batch, bool is_kxx);
+                          double* out /* rows_pad x Np */, int64_t out_stride, int batch, bool is_kxx, bool tiled = false);
 // potrf.cu
 int b7_launch_potrf(b7_gp* gp, int s0, int count);      // K -> L, beta, logdet, info for draws [s0,s0+count)
 int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
 // posterior.cu
-int b7_launch_posterior(b7_ctx* ctx, const double* Linv, const double* beta, int Np, const double* ks,
+int b7_launch_retile(b7_ctx* ctx, const double* fac, double* facT, int Np, int count);   // row-major -> tiled layout
+int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
 // score.cu
 int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,

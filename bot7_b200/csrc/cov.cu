@@ -16,14 +16,13 @@
 
 namespace {
 
-constexpr int kParStride = B7_MAX_DIMS + 4;
 constexpr int kRowsPerBlock = 32;
 
 template <int DT, int KERNEL>
 __global__ void __launch_bounds__(256)
 cov_kernel(const double* __restrict__ A, long long rows, long long rows_pad, int d, const double* __restrict__ Xt,
            int N, int Np, const double* __restrict__ par_base, long long par_stride, double* __restrict__ out_base,
-           long long out_stride, int is_kxx) {
+           long long out_stride, int is_kxx, int tiled) {
   __shared__ double s_a[kRowsPerBlock][DT];
   __shared__ double s_w[DT];
   const double* par = par_base + (long long)blockIdx.z * par_stride;
@@ -63,21 +62,27 @@ cov_kernel(const double* __restrict__ A, long long rows, long long rows_pad, int
       }
       if (is_kxx && row == k) val += diag_add;
     }
-    out[row * Np + k] = val;
+    if (tiled) {
+      // fragment order of gemm_tile.cuh: [row tile][k tile 16][k group 4][row 128][4]
+      const long long off = ((row >> 7) * (long long)(Np >> 4) + (k >> 4)) * 2048 + ((k >> 2) & 3) * 512 + (row & 127) * 4 + (k & 3);
+      out[off] = val;
+    } else {
+      out[row * Np + k] = val;
+    }
   }
 }
 
 template <int DT>
 int launch_dt(b7_ctx* ctx, int kernel, const double* A, long long rows, long long rows_pad, int d, const double* Xt,
               int N, int Np, const double* par, long long par_stride, double* out, long long out_stride, int batch,
-              bool is_kxx) {
+              bool is_kxx, bool tiled) {
   dim3 grid((Np + 255) / 256, (unsigned)((rows_pad + kRowsPerBlock - 1) / kRowsPerBlock), batch);
   if (kernel == B7_KERNEL_ARDSE)
     cov_kernel<DT, B7_KERNEL_ARDSE><<<grid, 256, 0, ctx->stream>>>(A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out,
-                                                                 out_stride, is_kxx);
+                                                                 out_stride, is_kxx, tiled);
   else
     cov_kernel<DT, B7_KERNEL_MATERN52><<<grid, 256, 0, ctx->stream>>>(A, rows, rows_pad, d, Xt, N, Np, par, par_stride,
-                                                                    out, out_stride, is_kxx);
+                                                                    out, out_stride, is_kxx, tiled);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;
@@ -87,12 +92,12 @@ int launch_dt(b7_ctx* ctx, int kernel, const double* A, long long rows, long lon
 
 int b7_launch_cov_batched(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d,
                           const double* Xt, int N, int Np, const double* par, int64_t par_stride, double* out,
-                          int64_t out_stride, int batch, bool is_kxx) {
+                          int64_t out_stride, int batch, bool is_kxx, bool tiled) {
   if (rows_pad <= 0) return 0;
   if (rows_pad / kRowsPerBlock + 1 > 65535) { b7_set_error("cov: too many rows per launch"); return B7_ERR_ARG; }
-  if (d <= 8) return launch_dt<8>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx);
-  if (d <= 16) return launch_dt<16>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx);
-  if (d <= 24) return launch_dt<24>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx);
-  return launch_dt<40>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx);
+  if (d <= 8) return launch_dt<8>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx, tiled);
+  if (d <= 16) return launch_dt<16>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx, tiled);
+  if (d <= 24) return launch_dt<24>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx, tiled);
+  return launch_dt<40>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, par_stride, out, out_stride, batch, is_kxx, tiled);
 }
 

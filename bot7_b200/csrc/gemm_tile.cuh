@@ -17,7 +17,14 @@
 
 namespace b7g {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
+#ifndef B7_BK
+#define B7_BK 16
+#endif
+#ifndef B7_STAGES
+#define B7_STAGES 4
+#endif
+constexpr int BM = 128, BN = 128, BK = B7_BK, STAGES = B7_STAGES, THREADS = 256;
+constexpr int KG = BK / 4;                            // k-groups of 4 per staged k-tile
 constexpr int OPERAND_DOUBLES = BM * BK;              // 2048 doubles = 16 KB
 constexpr int STAGE_DOUBLES = 2 * OPERAND_DOUBLES;    // A then B
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 128 KB
@@ -42,7 +49,7 @@ __device__ __forceinline__ void load_operand(double* s, const double* __restrict
   const double* src = g + (long long)row * ld + h * 2;
   double* dst = s + row * 4 + h * 2;
 #pragma unroll
-  for (int g4 = 0; g4 < 4; ++g4) cp_async16(dst + g4 * (BM * 4), src + g4 * 4);
+  for (int g4 = 0; g4 < KG; ++g4) cp_async16(dst + g4 * (BM * 4), src + g4 * 4);
 }
 
 struct Acc {
@@ -59,7 +66,7 @@ struct Acc {
 __device__ __forceinline__ void compute_stage(const double* __restrict__ sA, const double* __restrict__ sB, int wm,
                                               int wn, int lane, Acc& acc) {
 #pragma unroll
-  for (int g4 = 0; g4 < 4; ++g4) {
+  for (int g4 = 0; g4 < KG; ++g4) {
     double a[8], b[4];
     const double* pa = sA + g4 * (BM * 4) + (64 * wm) * 4 + lane;
     const double* pb = sB + g4 * (BN * 4) + (32 * wn) * 4 + lane;
@@ -101,6 +108,43 @@ __device__ __forceinline__ void mainloop(const double* __restrict__ gA, long lon
   }
   cp_wait<0>();
   __syncthreads();   // smem may be reused by the caller's epilogue
+}
+
+// ---- TMA bulk copies + mbarriers (used by the posterior pass) -------------------------------------
+// Operands can also live in HBM already in fragment order ("tiled layout"): tile (rb, kt) of a matrix
+// with Np columns is the 2048 contiguous doubles at ((rb * (Np/16) + kt) * 2048), ordered
+// [k-group][row][4].  One cp.async.bulk (SASS UBLKCP, executed by the TMA unit, no LSU issue slots)
+// then moves a whole 16 KB operand k-tile, completion is signalled on an mbarrier.
+constexpr int TILE_K = 16;
+constexpr int TILE_DOUBLES = BM * TILE_K;   // 2048
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;\n" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "B7_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra B7_DONE;\n\t"
+      "bra B7_WAIT;\n\t"
+      "B7_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;\n" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // coordinates of accumulator fragment (i, j) of this lane inside the 128x128 tile
