@@ -8,9 +8,9 @@
 //
 // Right-looking, block size 128 (= the DMMA tile edge of gemm_tile.cuh), row-major lower storage,
 // matrices padded to a multiple of 128 with identity.  Per block column j:
-//   diag  : one CTA per draw factors the 128x128 diagonal block with the rows held in registers and
-//           then inverts it (Gauss-Jordan forward elimination); it also produces x_j = L_jj^-1 r_j,
-//           the running log-determinant and info.
+//   diag  : one CTA per draw factors and inverts the 128x128 diagonal block inside shared memory,
+//           blocked by 16 so that the work is DMMA fragment products; it also produces
+//           x_j = L_jj^-1 r_j, the running log-determinant and info.
 //   panel : L21 = A21 * inv(L11)^T as DMMA tiles; the epilogue folds r_i -= L21 x_j, so the forward
 //           substitution for beta costs no extra pass over L.
 //   trail : A22 -= L21 L21^T on the lower tiles (DMMA).  Two-level blocking: inside an outer panel of
@@ -28,148 +28,182 @@ namespace {
 
 constexpr int NBK = B7_NB;          // 128
 constexpr int DIAG_THREADS = 512;
-// shared: Lcol[128][128] | pivs[128] | invs[128] | rowbuf[2][128] | rj[128] | xpart[4][128] | lg[128]
-constexpr int DIAG_SMEM = (NBK * NBK + 11 * NBK) * 8;
+constexpr int DIAG_WARPS = DIAG_THREADS / 32;
+constexpr int DLD = 132;            // 132 = 4 mod 16: DMMA fragment loads (row- and column-wise) are conflict free
+constexpr int SB = 16;              // sub-block width inside the 128 block
+constexpr int DSLD = 20;            // leading dimension of the 16x16 sub-block inverses
+constexpr int TLD = 68;             // scratch of the recursive inversion (64 x 68)
+// shared: M[128][132] | DS[8][16][20] | T[64][68] | LD[16][17] | pivs,invs,rj,lg [4][128]
+constexpr int DIAG_SMEM = (NBK * DLD + 8 * SB * DSLD + 64 * TLD + SB * 17 + 4 * NBK) * 8;
+
+// one 8x8 accumulator fragment: c += sign * A[m.., k0..k1) * op(B);  A row-major (k contiguous).
+// NN = false: B is [n][k] row-major (C = A B^T);  NN = true: B is [k][n] row-major (C = A B).
+template <bool NN>
+__device__ __forceinline__ void frag_mac(double& c0, double& c1, const double* __restrict__ A, int lda,
+                                         const double* __restrict__ B, int ldb, int k_begin, int k_end, double sign, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  for (int k = k_begin; k < k_end; k += 4) {
+    const double a = sign * A[r * lda + k + c];
+    const double b = NN ? B[(k + c) * ldb + r] : B[r * ldb + k + c];
+    dmma884(c0, c1, a, b);
+  }
+}
 
 // ---- diagonal block: potf2 + inverse + x_j + logdet + info -------------------------------------
-// Thread (r, part) keeps 32 entries of row r in registers (static indexing: the column loop is
-// unrolled in chunks of 32), so a step is one shared-memory column broadcast, one barrier and
-// 32 predicated DFMAs -- no read-modify-write chains through shared memory.  Two sweeps: the
-// right-looking Cholesky, then Gauss-Jordan forward elimination for the inverse.
+// Blocked inside shared memory so that almost all arithmetic is DMMA on 8x8 fragments:
+//   for each 16-wide sub-block: warp 0 factors the 16x16 diagonal piece in registers (shuffles) and
+//   inverts it; all warps then form the sub-panel L21 = A21 inv(L11)^T and the trailing update
+//   A22 -= L21 L21^T as fragment products.  The 128x128 inverse is assembled afterwards by
+//   recursive doubling ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]]) for h = 16, 32, 64,
+//   again as fragment products, in place.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, double* __restrict__ dinv,
             double* __restrict__ dinvT, long long dinv_stride, double* __restrict__ beta, double* __restrict__ logdet,
             int* __restrict__ info, int s0) {
-  extern __shared__ double sm[];
-  double* Lcol = sm;                       // Lcol[q*128 + r] = A[r][q] as it was when column q was eliminated
-  double* pivs = sm + NBK * NBK;
+  extern __shared__ __align__(16) double sm[];
+  double* M = sm;
+  double* DS = M + NBK * DLD;
+  double* T = DS + 8 * SB * DSLD;
+  double* LD = T + 64 * TLD;
+  double* pivs = LD + SB * 17;
   double* invs = pivs + NBK;
-  double* rowbuf = invs + NBK;             // [2][128]
-  double* rj = rowbuf + 2 * NBK;
-  double* xpart = rj + NBK;                // [4][128]
-  double* lg = xpart + 4 * NBK;
-  const int s = s0 + blockIdx.x, tid = threadIdx.x;
-  const int r = tid & 127, part = tid >> 7, c0 = part * 32;
+  double* rj = invs + NBK;
+  double* lg = rj + NBK;
+  const int s = s0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = lane >> 2, c = lane & 3;
   double* blk = fac + (long long)s * fac_stride + (long long)j * NBK * Np + (long long)j * NBK;
-  double a[32];
-  {
-    const double2* src = reinterpret_cast<const double2*>(blk + (long long)r * Np + c0);
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      double2 v = src[kk];
-      a[2 * kk] = v.x;
-      a[2 * kk + 1] = v.y;
-    }
+  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
+    const int i = e >> 7, k = e & 127;
+    M[i * DLD + k] = (k <= i) ? blk[(long long)i * Np + k] : 0.0;
   }
   if (tid < NBK) rj[tid] = beta[(long long)s * Np + j * NBK + tid];
   int my_info = 0;
-  // ---- sweep 1: Cholesky ----
-  for (int pq = 0; pq < 4; ++pq) {
+  __syncthreads();
+
+  for (int p = 0; p < NBK / SB; ++p) {
+    const int j0 = p * SB, i0 = j0 + SB, G = (NBK - i0) / 8;
+    // (a) 16x16 diagonal piece: factor (lane = row, column broadcast by shuffle), then invert by columns
+    if (warp == 0) {
+      double a[SB];
 #pragma unroll
-    for (int qq = 0; qq < 32; ++qq) {
-      const int q = pq * 32 + qq;
-      if (part == pq) Lcol[q * NBK + r] = a[qq];
-      __syncthreads();
-      const double piv = Lcol[q * NBK + q];
-      const double inv = rsqrt(piv);
-      if (tid == 0) {
-        pivs[q] = piv;
-        invs[q] = inv;
-        if (!(piv > 0.0) && my_info == 0) my_info = j * NBK + q + 1;
+      for (int k = 0; k < SB; ++k) a[k] = (lane < SB && k <= lane) ? M[(j0 + lane) * DLD + j0 + k] : 0.0;
+#pragma unroll
+      for (int q = 0; q < SB; ++q) {
+        const double piv = __shfl_sync(0xffffffffu, a[q], q);
+        const double inv = rsqrt(piv);
+        if (lane == 0) {
+          pivs[j0 + q] = piv;
+          invs[j0 + q] = inv;
+          if (!(piv > 0.0) && my_info == 0) my_info = j * NBK + j0 + q + 1;
+        }
+        const double my = a[q] * inv;   // L[lane][q] for lane > q
+#pragma unroll
+        for (int k = q + 1; k < SB; ++k) {
+          const double lk = __shfl_sync(0xffffffffu, my, k);
+          if (lane >= k) a[k] = fma(-my, lk, a[k]);
+        }
+        a[q] = (lane > q) ? my : (lane == q ? piv * inv : a[q]);
       }
-      const double arq = Lcol[q * NBK + r];
-      if (c0 + 31 > q) {   // warp-uniform: this 32-column slice still has columns right of q
-        const double t = arq * (inv * inv);   // A_rq / pivot
-        const double2* colv = reinterpret_cast<const double2*>(Lcol + q * NBK + c0);
+      if (lane < SB) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          double2 cv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) cv[u] = colv[h * 8 + u];   // broadcast loads, issued together
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int kk = h * 16 + 2 * u, k = c0 + kk;
-            const double n0 = fma(-t, cv[u].x, a[kk]), n1 = fma(-t, cv[u].y, a[kk + 1]);
-            a[kk] = (k > q && k <= r) ? n0 : a[kk];
-            a[kk + 1] = (k + 1 > q && k + 1 <= r) ? n1 : a[kk + 1];
-          }
+        for (int k = 0; k < SB; ++k) {
+          const double v = (k <= lane) ? a[k] : 0.0;
+          M[(j0 + lane) * DLD + j0 + k] = v;
+          LD[lane * 17 + k] = v;
         }
       }
-      if (part == pq) {
-        if (r > q) a[qq] = arq * inv;
-        else if (r == q) a[qq] = piv * inv;
+      __syncwarp();
+      // column `lane` of the inverse: x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii   (x_k = 0 for k < c)
+      double x[SB];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(-LD[i * 17 + k], x[k], acc);
+        x[i] = (i >= lane) ? acc * invs[j0 + i] : 0.0;
+      }
+      if (lane < SB) {
+#pragma unroll
+        for (int i = 0; i < SB; ++i) DS[(p * SB + i) * DSLD + lane] = x[i];
       }
     }
-  }
-  // L block back to global (upper part zeroed)
-  {
-    double2* dst = reinterpret_cast<double2*>(blk + (long long)r * Np + c0);
+    __syncthreads();
+    // (b) sub-panel: rows below, L21 = A21 * inv(L11)^T; one warp owns all 16 columns of its 8 rows
+    for (int g = warp; g < G; g += DIAG_WARPS) {
+      double* Arow = M + (i0 + 8 * g) * DLD + j0;
+      double a4[4];
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const int k = c0 + 2 * kk;
-      dst[kk] = make_double2(k <= r ? a[2 * kk] : 0.0, k + 1 <= r ? a[2 * kk + 1] : 0.0);
-    }
-  }
-  __syncthreads();   // invs complete
-  // ---- sweep 2: inverse by forward elimination, W starts as the identity ----
-  double w[32];
+      for (int k4 = 0; k4 < 4; ++k4) a4[k4] = Arow[r * DLD + 4 * k4 + c];
+      double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
 #pragma unroll
-  for (int kk = 0; kk < 32; ++kk) w[kk] = (c0 + kk == r) ? 1.0 : 0.0;
-  for (int pq = 0; pq < 4; ++pq) {
-#pragma unroll
-    for (int qq = 0; qq < 32; ++qq) {
-      const int q = pq * 32 + qq;
-      const double inv = invs[q];
-      double* buf = rowbuf + (q & 1) * NBK;
-      if (r == q) {
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          w[kk] *= inv;            // X[q][c] = W[q][c] / l_qq
-          buf[c0 + kk] = w[kk];
-        }
+      for (int k4 = 0; k4 < 4; ++k4) {
+        dmma884(c00, c01, a4[k4], DS[(p * SB + r) * DSLD + 4 * k4 + c]);
+        dmma884(c10, c11, a4[k4], DS[(p * SB + 8 + r) * DSLD + 4 * k4 + c]);
       }
-      __syncthreads();
-      if (c0 <= q) {   // warp-uniform: this slice has columns <= q
-        const double liq = Lcol[q * NBK + r] * inv;   // L[r][q]
-        const double2* rowv = reinterpret_cast<const double2*>(buf + c0);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          double2 rv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) rv[u] = rowv[h * 8 + u];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int kk = h * 16 + 2 * u, c = c0 + kk;
-            const double n0 = fma(-liq, rv[u].x, w[kk]), n1 = fma(-liq, rv[u].y, w[kk + 1]);
-            w[kk] = (r > q && c <= q) ? n0 : w[kk];
-            w[kk + 1] = (r > q && c + 1 <= q) ? n1 : w[kk + 1];
-          }
-        }
-      }
+      __syncwarp();
+      *reinterpret_cast<double2*>(Arow + r * DLD + 2 * c) = make_double2(c00, c01);
+      *reinterpret_cast<double2*>(Arow + r * DLD + 8 + 2 * c) = make_double2(c10, c11);
     }
+    __syncthreads();
+    // (c) trailing update on the lower fragments: A22 -= L21 L21^T
+    const int n_frag = G * (G + 1) / 2;
+    for (int f = warp; f < n_frag; f += DIAG_WARPS) {
+      int gi = 0, rem = f;
+      while (rem > gi) { rem -= gi + 1; ++gi; }
+      const int gk = rem;
+      double2* cp = reinterpret_cast<double2*>(M + (i0 + 8 * gi + r) * DLD + i0 + 8 * gk + 2 * c);
+      double2 cv = *cp;
+      frag_mac<false>(cv.x, cv.y, M + (i0 + 8 * gi) * DLD + j0, DLD, M + (i0 + 8 * gk) * DLD + j0, DLD, 0, SB, -1.0, lane);
+      *cp = cv;
+    }
+    __syncthreads();
   }
-  // x_j = inv(L_jj) r_j ; outputs
-  double xp = 0.0;
-#pragma unroll
-  for (int kk = 0; kk < 32; ++kk)
-    if (c0 + kk <= r) xp = fma(w[kk], rj[c0 + kk], xp);
-  xpart[part * NBK + r] = xp;
+  // L block back to global (upper part zero)
+  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
+    const int i = e >> 7, k = e & 127;
+    blk[(long long)i * Np + k] = (k <= i) ? M[i * DLD + k] : 0.0;
+  }
   if (tid < NBK) lg[tid] = log(pivs[tid] * invs[tid]);
-  double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  {
-    double2* dst = reinterpret_cast<double2*>(di + r * NBK + c0);
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      const int k = c0 + 2 * kk;
-      dst[kk] = make_double2(k <= r ? w[2 * kk] : 0.0, k + 1 <= r ? w[2 * kk + 1] : 0.0);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) dt[(c0 + kk) * NBK + r] = (c0 + kk <= r) ? w[kk] : 0.0;
+  __syncthreads();
+  // ---- inverse, in place: diagonal 16x16 pieces first, then recursive doubling ----
+  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
+    const int i = e >> 7, k = e & 127;
+    if ((i >> 4) == (k >> 4)) M[i * DLD + k] = DS[i * DSLD + (k & 15)];       // includes the zero upper part
+    else if (k > i) M[i * DLD + k] = 0.0;
   }
   __syncthreads();
-  if (tid < NBK)
-    beta[(long long)s * Np + j * NBK + tid] = ((xpart[tid] + xpart[NBK + tid]) + xpart[2 * NBK + tid]) + xpart[3 * NBK + tid];
+  for (int h = SB; h < NBK; h <<= 1) {
+    const int fpr = h / 8, n_pairs = NBK / (2 * h), per_pair = fpr * fpr;
+    // T = B * A^-1   (A^-1 lower triangular: k >= column fragment start)
+    for (int f = warp; f < n_pairs * per_pair; f += DIAG_WARPS) {
+      const int t = f / per_pair, fi = (f % per_pair) / fpr, fn = f % fpr, base = 2 * h * t;
+      double c0 = 0.0, c1 = 0.0;
+      frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base, DLD, M + base * DLD + base + 8 * fn, DLD, 8 * fn, h, 1.0, lane);
+      *reinterpret_cast<double2*>(T + (t * h + 8 * fi + r) * TLD + 8 * fn + 2 * c) = make_double2(c0, c1);
+    }
+    __syncthreads();
+    // X21 = -C^-1 * T  (C^-1 lower triangular: k < row fragment end)
+    for (int f = warp; f < n_pairs * per_pair; f += DIAG_WARPS) {
+      const int t = f / per_pair, fi = (f % per_pair) / fpr, fn = f % fpr, base = 2 * h * t;
+      double c0 = 0.0, c1 = 0.0;
+      frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base + h, DLD, T + (t * h) * TLD + 8 * fn, TLD, 0, 8 * fi + 8, -1.0, lane);
+      *reinterpret_cast<double2*>(M + (base + h + 8 * fi + r) * DLD + base + 8 * fn + 2 * c) = make_double2(c0, c1);
+    }
+    __syncthreads();
+  }
+  // x_j = inv(L_jj) r_j ; outputs
+  if (tid < NBK) {
+    double xv = 0.0;
+    for (int k = 0; k <= tid; ++k) xv = fma(M[tid * DLD + k], rj[k], xv);
+    beta[(long long)s * Np + j * NBK + tid] = xv;
+  }
+  double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
+    const int i = e >> 7, k = e & 127;
+    di[e] = (k <= i) ? M[i * DLD + k] : 0.0;
+    dt[e] = (k >= i) ? M[k * DLD + i] : 0.0;
+  }
   if (tid == 0) {
     double ld_acc = 0.0;
     for (int q = 0; q < NBK; ++q) ld_acc += lg[q];
