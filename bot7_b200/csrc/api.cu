@@ -66,12 +66,16 @@ int sync_removed(b7_grid* g) {
   return 0;
 }
 
+// tiled-layout helpers (gemm_tile.cuh): element (row, k) of a matrix with Np columns
+__device__ __forceinline__ long long tiled_index(int Np, int row, int k) {
+  return ((long long)(row >> 7) * (Np >> 4) + (k >> 4)) * 2048 + ((k >> 2) & 3) * 512 + (row & 127) * 4 + (k & 3);
+}
+
 __global__ void frob_rows_kernel(const double* __restrict__ A, int Np, int N, double* __restrict__ out) {
   // sum of squares of row blockIdx.x (first N columns), fixed-order tree
   __shared__ double sh[256];
   double s = 0.0;
-  const double* row = A + (long long)blockIdx.x * Np;
-  for (int k = threadIdx.x; k < N; k += blockDim.x) s += row[k] * row[k];
+  for (int k = threadIdx.x; k < N; k += blockDim.x) { const double v = A[tiled_index(Np, blockIdx.x, k)]; s += v * v; }
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -83,7 +87,7 @@ __global__ void frob_rows_kernel(const double* __restrict__ A, int Np, int N, do
 
 __global__ void identity_kernel(double* __restrict__ A, int Np) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < (long long)Np * Np) A[e] = (e / Np == e % Np) ? 1.0 : 0.0;
+  if (e < (long long)Np * Np) { const int row = (int)(e / Np), k = (int)(e % Np); A[tiled_index(Np, row, k)] = (row == k) ? 1.0 : 0.0; }
 }
 
 int upload_residual(b7_gp* gp, int s, const std::vector<double>& yh) {
@@ -101,7 +105,7 @@ int build_kxx(b7_gp* gp, int s0, int count) {
   StageTimer t(ctx, ST_KBUILD);
   B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, gp->X, gp->N, gp->Np, gp->d, gp->Xt, gp->N, gp->Np,
                                  gp->par + (size_t)s0 * kParStride, kParStride, gp->fac + (size_t)s0 * gp->Np * gp->Np,
-                                 (int64_t)gp->Np * gp->Np, count, true));
+                                 (int64_t)gp->Np * gp->Np, count, true, true));
   t.stop(1);
   return 0;
 }
@@ -153,7 +157,14 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaGetDeviceProperties(&p, device));
   ctx->sm_count = p.multiProcessorCount;
   if (p.major < 10) { b7_set_error("b7_init: device is sm_%d%d, this build is sm_100a only", p.major, p.minor); delete ctx; return B7_ERR_CUDA; }
-  B7_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // main stream at the highest priority: when the far trailing update (stream2) fills the machine, the
+  // small kernels of the next panel still get the first SMs that free up
+  int prio_lo = 0, prio_hi = 0;
+  B7_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+  B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo));
+  B7_CUDA(cudaEventCreateWithFlags(&ctx->evA, cudaEventDisableTiming));
+  B7_CUDA(cudaEventCreateWithFlags(&ctx->evB, cudaEventDisableTiming));
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));
@@ -169,6 +180,10 @@ void b7_shutdown(b7_ctx* ctx) {
   if (ctx->ks) cudaFree(ctx->ks);
   if (ctx->moments) cudaFree(ctx->moments);
   if (ctx->xs_stage) cudaFree(ctx->xs_stage);
+  cudaStreamSynchronize(ctx->stream2);
+  cudaEventDestroy(ctx->evA);
+  cudaEventDestroy(ctx->evB);
+  cudaStreamDestroy(ctx->stream2);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->tm0);
@@ -327,7 +342,7 @@ void b7_gp_free(b7_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
-  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facT, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (size_t i = 0; i < g_gp_host.size(); ++i)
     if (g_gp_host[i].first == gp) { delete g_gp_host[i].second; g_gp_host.erase(g_gp_host.begin() + i); break; }
@@ -432,22 +447,13 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
   B7_CHECK(b7_launch_trtri(gp, s0, count));
-  // tiled copy of L^-1 for the posterior pass (allocated on first use: logml-only fits never need it)
-  const size_t fs = (size_t)gp->Np * gp->Np;
-  if (!gp->facT) B7_CHECK(dev_alloc(&gp->facT, (size_t)gp->S * fs));
-  B7_CHECK(b7_launch_retile(ctx, gp->fac + (size_t)s0 * fs, gp->facT + (size_t)s0 * fs, gp->Np, count));
   t.stop((int)(ctx->launches - before));
   return 0;
 }
 
 int b7_gp_mark_ready(b7_gp* gp) {
   if (!gp) return B7_ERR_ARG;
-  // slots filled by the host (all-gather into fac): refresh the tiled copy of every draw
-  B7_CUDA(cudaSetDevice(gp->ctx->device));
-  const size_t fs = (size_t)gp->Np * gp->Np;
-  if (!gp->facT) B7_CHECK(dev_alloc(&gp->facT, (size_t)gp->S * fs));
-  B7_CHECK(b7_launch_retile(gp->ctx, gp->fac, gp->facT, gp->Np, gp->S));
-  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  // slots filled by the host (all-gather into fac, which already is the layout the posterior pass reads)
   gp->ready = true;
   gp->inverted = true;
   return 0;
@@ -543,9 +549,14 @@ int b7_gp_device_ptr(b7_gp* gp, int what, void** ptr, int64_t* bytes) {
 int b7_gp_read_factor(b7_gp* gp, int s, double* out_host) {
   if (!gp || !out_host || s < 0 || s >= gp->S) return B7_ERR_ARG;
   B7_CUDA(cudaSetDevice(gp->ctx->device));
-  B7_CUDA(cudaMemcpy2DAsync(out_host, (size_t)gp->N * 8, gp->fac + (size_t)s * gp->Np * gp->Np, (size_t)gp->Np * 8,
-                            (size_t)gp->N * 8, gp->N, cudaMemcpyDeviceToHost, gp->ctx->stream));
-  B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  double* tmp = nullptr;
+  B7_CHECK(dev_alloc(&tmp, (size_t)gp->N * gp->N));
+  int rc = b7_launch_untile(gp->ctx, gp->fac + (size_t)s * gp->Np * gp->Np, tmp, gp->Np, gp->N);
+  cudaError_t e = cudaMemcpyAsync(out_host, tmp, (size_t)gp->N * gp->N * 8, cudaMemcpyDeviceToHost, gp->ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(gp->ctx->stream);
+  cudaFree(tmp);
+  if (rc < 0) return rc;
+  if (e != cudaSuccess) { b7_set_error("gp_read_factor: %s", cudaGetErrorString(e)); return B7_ERR_CUDA; }
   return 0;
 }
 
@@ -563,7 +574,7 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   {
     StageTimer t(ctx, ST_POSTERIOR);
     const double* p = gp->par_host.data() + (size_t)s * kParStride;
-    B7_CHECK(b7_launch_posterior(ctx, gp->facT + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
+    B7_CHECK(b7_launch_posterior(ctx, gp->fac + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
                                  rp, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
     t.stop(1);
   }

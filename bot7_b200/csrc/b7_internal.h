@@ -34,6 +34,8 @@ struct b7_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                 // far trailing updates of the Cholesky (overlaps the next panel)
+  cudaEvent_t evA = nullptr, evB = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   double stage_ms[ST_COUNT] = {0};
   int64_t stage_calls[ST_COUNT] = {0};
@@ -68,12 +70,11 @@ struct b7_gp {
   double* y = nullptr;      // device N
   double* par = nullptr;    // device S x (B7_MAX_DIMS + 4): w[0..39], sf2, diag_add, m, sn2
   std::vector<double> par_host;
-  double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1 (row-major, lower)
-  double* facT = nullptr;   // device S x Np x Np : L^-1 in the tiled (fragment-order) layout read by the posterior pass
-  double* dinv = nullptr;   // device S x NB x 128 x 128 : inverse of the diagonal blocks of L
-  double* dinvT = nullptr;  // device, transposes of dinv
+  double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1, lower, in the tiled (fragment-order) layout
+  double* dinv = nullptr;   // device S x NB x (128 x 128 tiled) : inverse of the diagonal blocks of L
+  double* dinvT = nullptr;  // device, transposes of dinv (tiled)
   double* beta = nullptr;   // device S x Np : r -> L^-1 (y - m)
-  double* tt = nullptr;     // device S x 128 x Np : scratch of the inversion sweep
+  double* tt = nullptr;     // device S x (128 x Np tiled) : scratch of the inversion sweep
   double* logdet = nullptr; // device S : sum log L_ii
   int* info = nullptr;      // device S
   std::vector<double> jitter;
@@ -120,7 +121,7 @@ int b7_launch_cov_batched(b7_ctx* ctx, int kernel, const double* A /* rows x d *
 int b7_launch_potrf(b7_gp* gp, int s0, int count);      // K -> L, beta, logdet, info for draws [s0,s0+count)
 int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
 // posterior.cu
-int b7_launch_retile(b7_ctx* ctx, const double* fac, double* facT, int Np, int count);   // row-major -> tiled layout
+int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out /* N x N row-major */, int Np, int N);
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
 // score.cu

@@ -151,4 +151,76 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ int frag_row(int wm, int i, int lane) { return 64 * wm + 8 * i + (lane >> 2); }
 __device__ __forceinline__ int frag_col(int wn, int j, int lane) { return 32 * wn + 8 * j + 2 * (lane & 3); }
 
+// ---- tiled-layout addressing ---------------------------------------------------------------------
+// offset of tile (rb, kt) in a matrix with kt_all = Np/16 k-tiles per row block
+__host__ __device__ __forceinline__ long long tile_off(int kt_all, int rb, int kt) {
+  return ((long long)rb * kt_all + kt) * TILE_DOUBLES;
+}
+// offset of element (row, k) inside a run of consecutive k-tiles that starts at k = 0 (row < 128)
+__host__ __device__ __forceinline__ int elem_off(int row, int k) {
+  return (k >> 4) * TILE_DOUBLES + ((k >> 2) & 3) * (BM * 4) + row * 4 + (k & 3);
+}
+
+// ---- bulk-copy fed main loop -----------------------------------------------------------------------
+// acc += A * B^T where gA / gB point at runs of KT consecutive 16 KB tiles (tiled layout).  Thread 0 feeds
+// a ring of R_STAGES stages with two cp.async.bulk per stage, R_AHEAD stages ahead of its own consumption;
+// the 8 warps wait on the per-stage "full" mbarrier and release the stage through the "empty" one.
+constexpr int R_STAGES = 6, R_AHEAD = 4;
+constexpr int RING_BYTES = R_STAGES * 2 * TILE_DOUBLES * 8;   // 192 KB
+constexpr int RING_SMEM = RING_BYTES + 1024;                  // + 2 * R_STAGES barriers (and a little slack)
+
+struct Ring {
+  double* smem;
+  uint64_t *full, *empty;
+  long long issued, consumed;   // stage counters since init (identical in every thread; `issued` used by thread 0)
+  __device__ __forceinline__ void init(double* base) {
+    smem = base;
+    full = reinterpret_cast<uint64_t*>(base + R_STAGES * 2 * TILE_DOUBLES);
+    empty = full + R_STAGES;
+    issued = consumed = 0;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < R_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, THREADS / 32); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // thread 0 only
+  __device__ __forceinline__ void produce(const double* a_tile, const double* b_tile) {
+    const int slot = (int)(issued % R_STAGES);
+    if (issued >= R_STAGES) mbar_wait(empty + slot, (unsigned)(((issued / R_STAGES) - 1) & 1));
+    double* st = smem + slot * 2 * TILE_DOUBLES;
+    mbar_arrive_expect_tx(full + slot, 2 * TILE_DOUBLES * 8);
+    bulk_g2s(st, a_tile, TILE_DOUBLES * 8, full + slot);
+    bulk_g2s(st + TILE_DOUBLES, b_tile, TILE_DOUBLES * 8, full + slot);
+    ++issued;
+  }
+  __device__ __forceinline__ const double* wait_stage() {
+    const int slot = (int)(consumed % R_STAGES);
+    mbar_wait(full + slot, (unsigned)((consumed / R_STAGES) & 1));
+    return smem + slot * 2 * TILE_DOUBLES;
+  }
+  __device__ __forceinline__ void release_stage(int lane) {
+    const int slot = (int)(consumed % R_STAGES);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);
+    ++consumed;
+  }
+};
+
+// `already` = stages the caller has produced itself before calling (to overlap its own prologue)
+__device__ __forceinline__ void mainloop_bulk(Ring& ring, const double* __restrict__ gA, const double* __restrict__ gB, int KT,
+                                              Acc& acc, int already = 0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
+  int p = already < KT ? already : KT;
+  if (tid == 0)
+    for (; p < R_AHEAD && p < KT; ++p) ring.produce(gA + (long long)p * TILE_DOUBLES, gB + (long long)p * TILE_DOUBLES);
+  for (int kt = 0; kt < KT; ++kt) {
+    if (tid == 0 && p < KT) { ring.produce(gA + (long long)p * TILE_DOUBLES, gB + (long long)p * TILE_DOUBLES); ++p; }
+    const double* st = ring.wait_stage();
+    compute_stage(st, st + TILE_DOUBLES, wm, wn, lane, acc);
+    ring.release_stage(lane);
+  }
+  __syncthreads();   // every stage consumed: the ring memory may be reused by the caller's epilogue
+}
+
 }  // namespace b7g

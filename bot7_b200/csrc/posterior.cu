@@ -12,7 +12,7 @@
 // sum(v^2) and sum(v*beta) held in registers, and moves on.  V is never written.
 //
 // Data movement: both operands are kept in HBM in the fragment order of gemm_tile.cuh ("tiled
-// layout", written by retile_kernel for L^-1 and directly by the K* builder), so one k-step of an
+// layout": potrf.cu keeps the factor in it throughout, the K* builder writes it directly), so one k-step of an
 // operand is 16 contiguous KB.  One thread issues one cp.async.bulk (TMA unit) per operand per
 // stage and arms an mbarrier with the byte count; the 8 DMMA warps wait on that "full" barrier,
 // compute, and release the slot through an "empty" barrier.  There is no CTA-wide
@@ -137,31 +137,9 @@ posterior_kernel(const double* __restrict__ LinvT, const double* __restrict__ be
   }
 }
 
-// row-major lower factor -> tiled layout (only tiles at or below the diagonal are ever read)
-__global__ void __launch_bounds__(256)
-retile_kernel(const double* __restrict__ fac, double* __restrict__ facT, long long stride, int Np) {
-  const int rb = blockIdx.x, kb = blockIdx.y;          // 128x128 block (rb, kb), kb <= rb
-  if (kb > rb) return;
-  const double* src = fac + (long long)blockIdx.z * stride + (long long)rb * B7_NB * Np + (long long)kb * B7_NB;
-  double* dst = facT + (long long)blockIdx.z * stride + ((long long)rb * (Np / TILE_K) + (long long)kb * (B7_NB / TILE_K)) * TILE_DOUBLES;
-  for (int e = threadIdx.x; e < B7_NB * B7_NB; e += blockDim.x) {
-    // e enumerates the destination: [kt 8][g4 4][row 128][kk 4]
-    const int kk = e & 3, row = (e >> 2) & 127, g4 = (e >> 9) & 3, kt = e >> 11;
-    dst[e] = src[(long long)row * Np + kt * TILE_K + g4 * 4 + kk];
-  }
-}
-
 bool g_attr = false;
 
 }  // namespace
-
-int b7_launch_retile(b7_ctx* ctx, const double* fac, double* facT, int Np, int count) {
-  const int NB = Np / B7_NB;
-  retile_kernel<<<dim3(NB, NB, count), 256, 0, ctx->stream>>>(fac, facT, (long long)Np * Np, Np);
-  b7_count(ctx);
-  B7_CUDA(cudaGetLastError());
-  return 0;
-}
 
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT, const double* beta, int Np, const double* ksT,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var) {

@@ -6,8 +6,10 @@
 // gpTorch7's posterior.  One factor per slice-sampled hyper-parameter draw, all draws in one launch
 // sequence (grid.z / grid.x = draw).
 //
-// Right-looking, block size 128 (= the DMMA tile edge of gemm_tile.cuh), row-major lower storage,
-// matrices padded to a multiple of 128 with identity.  Per block column j:
+// Right-looking, block size 128 (= the DMMA tile edge of gemm_tile.cuh).  The matrices live in HBM in
+// the tiled (fragment-order) layout of gemm_tile.cuh from the moment K is built until L^-1 is read by
+// the posterior pass, so every operand k-step of every GEMM here is one 16 KB TMA bulk copy; lower
+// storage, padded to a multiple of 128 with identity.  Per block column j:
 //   diag  : one CTA per draw factors and inverts the 128x128 diagonal block inside shared memory,
 //           blocked by 16 so that the work is DMMA fragment products; it also produces
 //           x_j = L_jj^-1 r_j, the running log-determinant and info.
@@ -19,6 +21,8 @@
 //           long-k launches with a quarter of the read-modify-write traffic on C.
 // Inversion (LAPACK dtrtri order, in place, column sweep from the right):
 //   T = L[j+1:, j] * inv(L_jj)  (stored transposed), then  X[j+1:, j] = -Linv[j+1:, j+1:] * T.
+#include <stdlib.h>
+
 #include "b7_internal.h"
 #include "gemm_tile.cuh"
 
@@ -71,10 +75,11 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
   double* lg = rj + NBK;
   const int s = s0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, c = lane & 3;
-  double* blk = fac + (long long)s * fac_stride + (long long)j * NBK * Np + (long long)j * NBK;
+  double* blk = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, j, j * (NBK / TILE_K));   // 8 tiles of block (j, j)
   for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    const int i = e >> 7, k = e & 127;
-    M[i * DLD + k] = (k <= i) ? blk[(long long)i * Np + k] : 0.0;
+    // e enumerates the tiled order [kt][g4][row][kk]
+    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
+    M[i * DLD + k] = (k <= i) ? blk[e] : 0.0;
   }
   if (tid < NBK) rj[tid] = beta[(long long)s * Np + j * NBK + tid];
   int my_info = 0;
@@ -160,8 +165,8 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
   }
   // L block back to global (upper part zero)
   for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    const int i = e >> 7, k = e & 127;
-    blk[(long long)i * Np + k] = (k <= i) ? M[i * DLD + k] : 0.0;
+    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
+    blk[e] = (k <= i) ? M[i * DLD + k] : 0.0;
   }
   if (tid < NBK) lg[tid] = log(pivs[tid] * invs[tid]);
   __syncthreads();
@@ -199,8 +204,8 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
   }
   double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
   double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    const int i = e >> 7, k = e & 127;
+  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {   // both in tiled order, ready to be GEMM operands
+    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
     di[e] = (k <= i) ? M[i * DLD + k] : 0.0;
     dt[e] = (k >= i) ? M[k * DLD + i] : 0.0;
   }
@@ -217,12 +222,13 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
 __global__ void __launch_bounds__(THREADS, 1)
 panel_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, const double* __restrict__ dinv,
              long long dinv_stride, double* __restrict__ beta, int s0) {
-  extern __shared__ __align__(16) double smem[];
-  const int s = s0 + blockIdx.z, it = j + 1 + blockIdx.x;
-  double* tile = fac + (long long)s * fac_stride + (long long)it * NBK * Np + (long long)j * NBK;
+  extern __shared__ __align__(128) double smem[];
+  const int s = s0 + blockIdx.z, it = j + 1 + blockIdx.x, KPB = NBK / TILE_K;
+  double* tile = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, it, j * KPB);
   const double* B = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  Ring ring; ring.init(smem);
   Acc acc; acc.zero();
-  mainloop(tile, Np, B, NBK, NBK / BK, smem, acc);
+  mainloop_bulk(ring, tile, B, KPB, acc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
   const double* xj = beta + (long long)s * Np + j * NBK;
   double* red = smem;   // [128][4]
@@ -233,7 +239,7 @@ panel_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, cons
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int col = frag_col(wn, jj, lane);
-      *reinterpret_cast<double2*>(tile + (long long)row * Np + col) = make_double2(acc.c[i][jj][0], acc.c[i][jj][1]);
+      *reinterpret_cast<double2*>(tile + elem_off(row, col)) = make_double2(acc.c[i][jj][0], acc.c[i][jj][1]);
       part += acc.c[i][jj][0] * xj[col] + acc.c[i][jj][1] * xj[col + 1];
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -253,57 +259,68 @@ panel_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, cons
 // tiles to its right: the long-k launches carry most of the flops with one read-modify-write of C.
 __global__ void __launch_bounds__(THREADS, 1)
 trail_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, int kb1, int it0, int nt0, int s0) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int it = it0 + blockIdx.x, nt = nt0 + blockIdx.y;
   if (nt > it) return;
-  const int s = s0 + blockIdx.z;
+  const int s = s0 + blockIdx.z, KPB = NBK / TILE_K, KTA = Np / TILE_K;
   double* base = fac + (long long)s * fac_stride;
-  const double* A = base + (long long)it * NBK * Np + (long long)kb0 * NBK;
-  const double* B = base + (long long)nt * NBK * Np + (long long)kb0 * NBK;
-  double* C = base + (long long)it * NBK * Np + (long long)nt * NBK;
-  Acc acc; acc.zero();
-  mainloop(A, Np, B, Np, (kb1 - kb0) * (NBK / BK), smem, acc);
+  const double* A = base + tile_off(KTA, it, kb0 * KPB);
+  const double* B = base + tile_off(KTA, nt, kb0 * KPB);
+  double* C = base + tile_off(KTA, it, nt * KPB);
+  Ring ring; ring.init(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+  if (threadIdx.x == 0)   // start the operand stream before touching C
+    for (int p = 0; p < 2 && p < (kb1 - kb0) * KPB; ++p) ring.produce(A + (long long)p * TILE_DOUBLES, B + (long long)p * TILE_DOUBLES);
+  // acc starts at -C (loaded while the first bulk copies are in flight), accumulates +A B^T, and C_new = -acc:
+  // the read of C is off the critical path and the epilogue is stores only
+  Acc acc;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      double2* p = reinterpret_cast<double2*>(C + (long long)frag_row(wm, i, lane) * Np + frag_col(wn, jj, lane));
-      double2 v = *p;
-      v.x -= acc.c[i][jj][0];
-      v.y -= acc.c[i][jj][1];
-      *p = v;
+      const double2 v = *reinterpret_cast<const double2*>(C + elem_off(frag_row(wm, i, lane), frag_col(wn, jj, lane)));
+      acc.c[i][jj][0] = -v.x;
+      acc.c[i][jj][1] = -v.y;
     }
+  mainloop_bulk(ring, A, B, (kb1 - kb0) * KPB, acc, 2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      *reinterpret_cast<double2*>(C + elem_off(frag_row(wm, i, lane), frag_col(wn, jj, lane))) =
+          make_double2(-acc.c[i][jj][0], -acc.c[i][jj][1]);
 }
 
 // ---- inversion sweep ------------------------------------------------------------------------------
 __global__ void place_diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, const double* __restrict__ dinv,
                                   long long dinv_stride, int s0) {
   const int s = s0 + blockIdx.y, j = blockIdx.x;
-  double* blk = fac + (long long)s * fac_stride + (long long)j * NBK * Np + (long long)j * NBK;
+  double* blk = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, j, j * (NBK / TILE_K));
   const double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  for (int e = threadIdx.x; e < NBK * NBK; e += blockDim.x) blk[(long long)(e >> 7) * Np + (e & 127)] = di[e];
+  for (int e = threadIdx.x; e < NBK * NBK; e += blockDim.x) blk[e] = di[e];   // same tiled order on both sides
 }
 
-// T = L[it, j] * inv(L_jj), written transposed: tt[c][it*128 + row]
+// T = L[it, j] * inv(L_jj), written transposed into the one-row-block tiled matrix tt (128 x Np):
+// tt(c, it*128 + row) = T(row, c)
 __global__ void __launch_bounds__(THREADS, 1)
 inv_step1_kernel(const double* __restrict__ fac, long long fac_stride, int Np, int j, const double* __restrict__ dinvT,
                  long long dinv_stride, double* __restrict__ tt, long long tt_stride, int s0) {
-  extern __shared__ __align__(16) double smem[];
-  const int s = s0 + blockIdx.z, it = j + 1 + blockIdx.x;
-  const double* A = fac + (long long)s * fac_stride + (long long)it * NBK * Np + (long long)j * NBK;
+  extern __shared__ __align__(128) double smem[];
+  const int s = s0 + blockIdx.z, it = j + 1 + blockIdx.x, KPB = NBK / TILE_K;
+  const double* A = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, it, j * KPB);
   const double* B = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  Ring ring; ring.init(smem);
   Acc acc; acc.zero();
-  mainloop(A, Np, B, NBK, NBK / BK, smem, acc);
+  mainloop_bulk(ring, A, B, KPB, acc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
-  double* T = tt + (long long)s * tt_stride + (long long)it * NBK;
+  double* T = tt + (long long)s * tt_stride;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      const int row = frag_row(wm, i, lane), col = frag_col(wn, jj, lane);
-      T[(long long)col * Np + row] = acc.c[i][jj][0];
-      T[(long long)(col + 1) * Np + row] = acc.c[i][jj][1];
+      const int k = it * NBK + frag_row(wm, i, lane), col = frag_col(wn, jj, lane);
+      T[elem_off(col, k)] = acc.c[i][jj][0];
+      T[elem_off(col + 1, k)] = acc.c[i][jj][1];
     }
 }
 
@@ -311,34 +328,41 @@ inv_step1_kernel(const double* __restrict__ fac, long long fac_stride, int Np, i
 __global__ void __launch_bounds__(THREADS, 1)
 inv_step2_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, const double* __restrict__ tt,
                  long long tt_stride, int s0) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   // longest rows first: better tail behaviour
-  const int n_it = gridDim.x, it = j + n_it - (int)blockIdx.x;
+  const int n_it = gridDim.x, it = j + n_it - (int)blockIdx.x, KPB = NBK / TILE_K, KTA = Np / TILE_K;
   const int s = s0 + blockIdx.z;
   double* base = fac + (long long)s * fac_stride;
-  const long long k0 = (long long)(j + 1) * NBK;
-  const double* A = base + (long long)it * NBK * Np + k0;
-  const double* B = tt + (long long)s * tt_stride + k0;
-  double* C = base + (long long)it * NBK * Np + (long long)j * NBK;
+  const double* A = base + tile_off(KTA, it, (j + 1) * KPB);
+  const double* B = tt + (long long)s * tt_stride + (long long)(j + 1) * KPB * TILE_DOUBLES;
+  double* C = base + tile_off(KTA, it, j * KPB);
+  Ring ring; ring.init(smem);
   Acc acc; acc.zero();
-  mainloop(A, Np, B, Np, (it - j) * (NBK / BK), smem, acc);
+  mainloop_bulk(ring, A, B, (it - j) * KPB, acc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
-      *reinterpret_cast<double2*>(C + (long long)frag_row(wm, i, lane) * Np + frag_col(wn, jj, lane)) =
+      *reinterpret_cast<double2*>(C + elem_off(frag_row(wm, i, lane), frag_col(wn, jj, lane))) =
           make_double2(-acc.c[i][jj][0], -acc.c[i][jj][1]);
+}
+
+// tiled <-> row-major conversion of the N x N leading part (tests, b7_gp_read_factor)
+__global__ void untile_kernel(const double* __restrict__ facT, double* __restrict__ out, int Np, int N) {
+  const int row = blockIdx.x;
+  const double* src = facT + tile_off(Np / TILE_K, row >> 7, 0);
+  for (int k = threadIdx.x; k < N; k += blockDim.x) out[(long long)row * N + k] = src[elem_off(row & 127, k)];
 }
 
 bool g_attr_done = false;
 int set_attrs() {
   if (g_attr_done) return 0;
   B7_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  B7_CUDA(cudaFuncSetAttribute(trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  B7_CUDA(cudaFuncSetAttribute(inv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  B7_CUDA(cudaFuncSetAttribute(inv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  B7_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+  B7_CUDA(cudaFuncSetAttribute(trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+  B7_CUDA(cudaFuncSetAttribute(inv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+  B7_CUDA(cudaFuncSetAttribute(inv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   g_attr_done = true;
   return 0;
 }
@@ -350,29 +374,52 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   B7_CHECK(set_attrs());
   const int Np = gp->Np, NB = gp->NB;
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK;
-  const int W = 4;   // outer panel = 4 blocks (512 columns)
+  static const int W_env = getenv("B7_POTRF_W") ? atoi(getenv("B7_POTRF_W")) : 0;
+  const int W = W_env > 0 ? W_env : 4;   // outer panel = 4 blocks (512 columns)
+  cudaStream_t sa = ctx->stream, sb = ctx->stream2;
+  bool far_pending = false;
   for (int J = 0; J < NB; J += W) {
     const int Jend = J + W < NB ? J + W : NB;
+    // --- the panel's own columns: latency-bound chain on the main stream ---
     for (int j = J; j < Jend; ++j) {
-      diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, gp->dinvT, ds, gp->beta,
-                                                                  gp->logdet, gp->info, s0);
+      diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, gp->dinvT, ds, gp->beta,
+                                                        gp->logdet, gp->info, s0);
       b7_count(ctx);
       const int rem = NB - 1 - j;
       if (rem > 0) {
-        panel_kernel<<<dim3(rem, 1, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
+        panel_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
         b7_count(ctx);
       }
       if (Jend - 1 - j > 0) {   // columns j+1 .. Jend-1 of the outer panel, all rows below
-        trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
+        trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
         b7_count(ctx);
       }
     }
-    const int right = NB - Jend;
-    if (right > 0) {
-      trail_kernel<<<dim3(right, right, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
+    if (Jend >= NB) break;
+    // --- update by this panel (k = 512).  "near": the next panel's columns, needed at once, main stream
+    //     (after the previous far update, which touched the same tiles).  "far": everything to the right of
+    //     the next panel, on the second stream, overlapping the next panel's chain of small kernels. ---
+    const int near_end = Jend + W < NB ? Jend + W : NB;
+    if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+    trail_kernel<<<dim3(NB - Jend, near_end - Jend, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
+    b7_count(ctx);
+    if (near_end < NB) {
+      B7_CUDA(cudaEventRecord(ctx->evA, sa));
+      B7_CUDA(cudaStreamWaitEvent(sb, ctx->evA, 0));
+      trail_kernel<<<dim3(NB - near_end, NB - near_end, count), THREADS, RING_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
       b7_count(ctx);
+      B7_CUDA(cudaEventRecord(ctx->evB, sb));
+      far_pending = true;
     }
   }
+  if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out, int Np, int N) {
+  untile_kernel<<<N, 256, 0, ctx->stream>>>(facT, out, Np, N);
+  b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;
 }
@@ -386,8 +433,8 @@ int b7_launch_trtri(b7_gp* gp, int s0, int count) {
   b7_count(ctx);
   for (int j = NB - 2; j >= 0; --j) {
     const int rem = NB - 1 - j;
-    inv_step1_kernel<<<dim3(rem, 1, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinvT, ds, gp->tt, ts, s0);
-    inv_step2_kernel<<<dim3(rem, 1, count), THREADS, SMEM_BYTES, ctx->stream>>>(gp->fac, fs, Np, j, gp->tt, ts, s0);
+    inv_step1_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinvT, ds, gp->tt, ts, s0);
+    inv_step2_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->tt, ts, s0);
     b7_count(ctx, 2);
   }
   B7_CUDA(cudaGetLastError());
