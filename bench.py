@@ -227,6 +227,15 @@ def main():
         if rep == 0:
             f.free()
     assert (f.info == 0).all()
+    # single-factor density evaluation (the slice sampler's f): X, y resident, new hyper-parameters each call
+    f1 = models.GPFactors(Xo, y, hyp[:1], "ardse", False, L.FIT_LOGML_ONLY, ctx)
+    for i in range(2):
+        f1.refit(hyp[1:2], L.FIT_LOGML_ONLY)
+    t0 = time.perf_counter()
+    for i in range(5):
+        f1.refit(hyp[i:i + 1], L.FIT_LOGML_ONLY)
+    fit_ms["single_factor_refit_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+    f1.free()
 
     def step():
         o_, b_, n_ = C.c_int64(), C.c_double(), C.c_int64()

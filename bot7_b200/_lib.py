@@ -51,6 +51,7 @@ SIGNATURES = {
     "b7_grid_original_index": (_i, [_p, _l, _lp]),
     "b7_grid_free": (None, [_p]),
     "b7_gp_fit": (_i, [_p, _i, _dp, _dp, _i, _i, _dp, _i, _i, _i, _i, C.POINTER(_p), _ip, _dp, _dp]),
+    "b7_gp_refit": (_i, [_p, _dp, _i, _ip, _dp, _dp]),
     "b7_gp_num_draws": (_i, [_p]),
     "b7_gp_num_obs": (_i, [_p]),
     "b7_gp_predict": (_i, [_p, _i, _dp, _l, _dp, _dp]),

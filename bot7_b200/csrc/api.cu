@@ -355,6 +355,30 @@ int b7_gp_padded_n(b7_gp* gp) { return gp ? gp->Np : 0; }
 
 static int gp_retry_draw(b7_gp* gp, int s, int first_info);
 
+// parameters per draw (oracle/SPEC.md): w = exp(-log l), sf2 = exp(2 log sf), sn2 = exp(2 log sn)
+static void set_hypers_host(b7_gp* gp, const double* hyp) {
+  const int d = gp->d, H = d + 3, S = gp->S;
+  gp->par_host.assign((size_t)S * kParStride, 0.0);
+  for (int s = 0; s < S; ++s) {
+    const double* h = hyp + (size_t)s * H;
+    double* p = gp->par_host.data() + (size_t)s * kParStride;
+    for (int i = 0; i < d; ++i) p[i] = exp(-h[i]);
+    const double sf2 = exp(2.0 * h[d]), sn2 = exp(2.0 * h[d + 1]);
+    p[B7_MAX_DIMS] = sf2;
+    p[B7_MAX_DIMS + 1] = sn2 + (gp->noiseless ? 1e-8 * sf2 : 0.0);
+    p[B7_MAX_DIMS + 2] = h[d + 2];
+    p[B7_MAX_DIMS + 3] = sn2;
+  }
+}
+
+static void residuals_host(b7_gp* gp, const std::vector<double>& y, std::vector<double>& r) {
+  r.assign((size_t)gp->S * gp->Np, 0.0);
+  for (int s = 0; s < gp->S; ++s) {
+    const double m = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 2];
+    for (int i = 0; i < gp->N; ++i) r[(size_t)s * gp->Np + i] = y[i] - m;
+  }
+}
+
 int b7_gp_fit_range(b7_gp* gp, int s0, int count, int* info, double* logml, double* jitter) {
   if (!gp || s0 < 0 || count < 0 || s0 + count > gp->S) { b7_set_error("gp_fit_range: draw range"); return B7_ERR_ARG; }
   b7_ctx* ctx = gp->ctx;
@@ -485,25 +509,11 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
   GpHostCopy* hc = new GpHostCopy();
   hc->y.assign(y, y + N);
   g_gp_host.push_back({gp, hc});
-  // parameters per draw (oracle/SPEC.md): w = exp(-log l), sf2 = exp(2 log sf), sn2 = exp(2 log sn)
-  gp->par_host.assign((size_t)S * kParStride, 0.0);
-  for (int s = 0; s < S; ++s) {
-    const double* h = hyp + (size_t)s * H;
-    double* p = gp->par_host.data() + (size_t)s * kParStride;
-    for (int i = 0; i < d; ++i) p[i] = exp(-h[i]);
-    const double sf2 = exp(2.0 * h[d]), sn2 = exp(2.0 * h[d + 1]);
-    p[B7_MAX_DIMS] = sf2;
-    p[B7_MAX_DIMS + 1] = sn2 + (noiseless ? 1e-8 * sf2 : 0.0);
-    p[B7_MAX_DIMS + 2] = h[d + 2];
-    p[B7_MAX_DIMS + 3] = sn2;
-  }
-  std::vector<double> xt((size_t)d * Np, 0.0), r((size_t)S * Np, 0.0);
+  set_hypers_host(gp, hyp);
+  std::vector<double> xt((size_t)d * Np, 0.0), r;
   for (int i = 0; i < N; ++i)
     for (int k = 0; k < d; ++k) xt[(size_t)k * Np + i] = X[(size_t)i * d + k];
-  for (int s = 0; s < S; ++s) {
-    const double m = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 2];
-    for (int i = 0; i < N; ++i) r[(size_t)s * Np + i] = y[i] - m;
-  }
+  residuals_host(gp, hc->y, r);
   cudaStream_t st = ctx->stream;
   cudaError_t e;
   if ((e = cudaMemcpyAsync(gp->X, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
@@ -524,6 +534,31 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { b7_set_error("gp_fit: %s", cudaGetErrorString(e)); return fail(B7_ERR_CUDA); }
   gp->ready = true;
   *out = gp;
+  return 0;
+}
+
+// Same observations, new hyper-parameter draws: the slice sampler's density evaluation
+// (samplers/slice.lua:100-103) with X, y and every buffer resident -- only S x H doubles go in and
+// S log-likelihoods come out.
+int b7_gp_refit(b7_gp* gp, const double* hyp, int flags, int* info, double* logml, double* jitter) {
+  if (!gp || !hyp || (flags != B7_FIT_PREDICT && flags != B7_FIT_LOGML_ONLY)) { b7_set_error("gp_refit: bad arguments"); return B7_ERR_ARG; }
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  GpHostCopy* hc = host_copy(gp);
+  set_hypers_host(gp, hyp);
+  std::vector<double> r;
+  residuals_host(gp, hc->y, r);
+  gp->ready = false; gp->inverted = false;
+  B7_CUDA(cudaMemcpyAsync(gp->par, gp->par_host.data(), gp->par_host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  B7_CUDA(cudaMemcpyAsync(gp->beta, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  B7_CHECK(b7_gp_fit_range(gp, 0, gp->S, info, logml, jitter));
+  if (flags == B7_FIT_PREDICT) {
+    B7_CHECK(gp_invert(gp, 0, gp->S));
+    gp->inverted = true;
+  }
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  gp->ready = true;
   return 0;
 }
 

@@ -142,9 +142,10 @@ blr_moments_kernel(const double* __restrict__ Z, long long M, int D, const doubl
                    const double* __restrict__ w, const double* __restrict__ par, int S, long long ld_out,
                    double* __restrict__ mean, double* __restrict__ var) {
   extern __shared__ __align__(16) double sh[];
-  double* Ls = sh;                    // DP x DP (row-major, zero padded)
+  // the staged candidate tile is only needed until the features sit in registers; L^-1 then reuses the space
+  double* zt = sh;                    // 128 x (D | 1) staged tile
+  double* Ls = sh;                    // DP x DP (transposed, zero padded)
   double* ws = Ls + DP * DP;          // DP
-  double* zt = ws + DP;               // 128 x (D | 1) staged tile
   const int ldz = D | 1;              // odd stride: conflict-free row reads
   const int tid = threadIdx.x;
   const long long c0 = (long long)blockIdx.x * 128;
@@ -157,7 +158,7 @@ blr_moments_kernel(const double* __restrict__ Z, long long M, int D, const doubl
   for (int s = 0; s < S; ++s) {
     __syncthreads();
     for (int e = tid; e < DP * DP; e += 128) {
-      const int i = e / DP, k = e % DP;
+      const int k = e / DP, i = e % DP;          // stored transposed: Ls[k][i] = Linv[i][k]
       Ls[e] = (i < D && k < D) ? Linv[(long long)s * D * D + i * D + k] : 0.0;
     }
     if (tid < DP) ws[tid] = tid < D ? w[(long long)s * D + tid] : 0.0;
@@ -165,12 +166,25 @@ blr_moments_kernel(const double* __restrict__ Z, long long M, int D, const doubl
     double s2 = 0.0, mu = 0.0;
 #pragma unroll
     for (int k = 0; k < DP; ++k) mu = fma(ws[k], phi[k], mu);
+    // four rows of v = Linv phi at a time: four independent FMA chains, and for a fixed k the four
+    // matrix entries Linv[i..i+3][k] are 32 contiguous bytes of the transposed copy (two LDS.128 broadcasts)
 #pragma unroll
-    for (int i = 0; i < DP; ++i) {
-      double v = 0.0;
+    for (int i = 0; i < DP; i += 4) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
-      for (int k = 0; k <= i; ++k) v = fma(Ls[i * DP + k], phi[k], v);
-      s2 = fma(v, v, s2);
+      for (int k = 0; k < i + 4; ++k) {
+        const double2 l01 = *reinterpret_cast<const double2*>(Ls + k * DP + i);
+        const double2 l23 = *reinterpret_cast<const double2*>(Ls + k * DP + i + 2);
+        const double p = phi[k];
+        v0 = fma(l01.x, p, v0);   // entries above the diagonal are zero in the padded copy
+        v1 = fma(l01.y, p, v1);
+        v2 = fma(l23.x, p, v2);
+        v3 = fma(l23.y, p, v3);
+      }
+      s2 = fma(v0, v0, s2);
+      s2 = fma(v1, v1, s2);
+      s2 = fma(v2, v2, s2);
+      s2 = fma(v3, v3, s2);
     }
     if (tid < nc) {
       mean[(long long)s * ld_out + c0 + tid] = par[s * 4 + 2] + mu;
@@ -182,7 +196,8 @@ blr_moments_kernel(const double* __restrict__ Z, long long M, int D, const doubl
 template <int DP>
 int launch_moments_dp(b7_ctx* ctx, const double* Z, int64_t M, int D, const b7_blr* blr, int s0, int S, int64_t ld_out,
                       double* mean, double* var) {
-  const size_t smem = ((size_t)DP * DP + DP + 128 * (size_t)(D | 1)) * 8;
+  const size_t a = ((size_t)DP * DP + DP) * 8, b = 128 * (size_t)(D | 1) * 8;
+  const size_t smem = a > b ? a : b;
   static bool done = false;
   if (!done) {
     B7_CUDA(cudaFuncSetAttribute(blr_moments_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

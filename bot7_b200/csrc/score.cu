@@ -27,7 +27,7 @@ __device__ __forceinline__ double erf_ref(double x) {
   // utils/math.lua:261-288
   const double c1 = 0.254829592, c2 = -0.284496736, c3 = 1.421413741, c4 = -1.453152027, c5 = 1.061405429,
                p = 0.3275911;
-  double t = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(fabs(x), p), 1.0));
+  double t = __drcp_rn(__dadd_rn(__dmul_rn(fabs(x), p), 1.0));   // correctly rounded 1/x == pow(x, -1)
   double r = __dmul_rn(t, c5);
   r = __dadd_rn(r, c4); r = __dmul_rn(r, t);
   r = __dadd_rn(r, c3); r = __dmul_rn(r, t);

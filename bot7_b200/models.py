@@ -52,6 +52,17 @@ class GPFactors:
                 print("Warning: utils.math.chol succeeded in factorizing the\ninput matrix after applying "
                       "a jitter of %.2e" % self.jitter[s])
 
+    def refit(self, hyp, flags=L.FIT_PREDICT):
+        """New hyper-parameter draws on the same observations; all device buffers are reused."""
+        hyp = np.atleast_2d(L.as_f64(hyp))
+        if hyp.shape != self.hyp.shape:
+            raise ValueError("refit needs the same S x H shape as the original fit")
+        info = (C.c_int * self.S)()
+        L.check(L.lib().b7_gp_refit(self.handle, L.dptr(hyp), flags, info, L.dptr(self.logml), L.dptr(self.jitter)), "b7_gp_refit")
+        self.hyp = hyp
+        self.info = np.array(list(info), dtype=np.int32)
+        return self
+
     def predict(self, s, Xs):
         Xs = L.as_f64(Xs)
         if Xs.ndim == 1:
@@ -117,6 +128,8 @@ class gp_regressor:
         self.hyp = None
         self._cache_key = None
         self._factors = None
+        self._density_key = None
+        self._density = None
 
     def class_(self):
         return "gp.models.gp_regressor"
@@ -144,9 +157,16 @@ class gp_regressor:
         """log p(y | h) + log p(h): one density evaluation of the slice sampler = one GP fit
         (K build + potrf + beta + logdet) with nothing but a scalar coming back."""
         h = L.as_f64(h).reshape(1, -1)
-        f = GPFactors(X, Y, h, self.config["kernel"], self.config["noiseless"], L.FIT_LOGML_ONLY, self.ctx)
+        key = (np.asarray(X).tobytes(), np.asarray(Y).tobytes())
+        if self._density_key != key:                 # X, y stay resident across the sampler's evaluations
+            if self._density is not None:
+                self._density.free()
+            self._density = GPFactors(X, Y, h, self.config["kernel"], self.config["noiseless"], L.FIT_LOGML_ONLY, self.ctx)
+            self._density_key = key
+        else:
+            self._density.refit(h, L.FIT_LOGML_ONLY)
+        f = self._density
         lp = float(f.logml[0]) if f.info[0] == 0 and np.isfinite(f.logml[0]) else -np.inf
-        f.free()
         sd = self.config["prior_std"]
         return lp - 0.5 * float(np.sum((h / sd) ** 2))
 

@@ -85,6 +85,10 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
               const double* hyp, int S, int H, int noiseless, int flags,
               b7_gp** out, int* info /* S, nullable */, double* logml /* S, nullable */,
               double* jitter /* S, nullable */);
+/* Same observations, new S x H hyper-parameter draws, every device buffer reused: the density
+ * evaluation of the slice sampler (samplers/slice.lua:100-103) with X and y resident.
+ * flags: B7_FIT_PREDICT or B7_FIT_LOGML_ONLY. */
+int b7_gp_refit(b7_gp* gp, const double* hyp, int flags, int* info, double* logml, double* jitter);
 int b7_gp_num_draws(b7_gp* gp);
 int b7_gp_num_obs(b7_gp* gp);
 /* model:predict(X_obs,Y_obs,X_hid,hyp,{mean,var}) for draw s (0-based): M x d host points ->

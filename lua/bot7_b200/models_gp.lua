@@ -42,9 +42,17 @@ function model:predict(X0, Y0, X1, hyp, req)
   return {mean = mean, var = var}
 end
 
--- log p(y | hyp): the density the slice sampler evaluates (samplers/slice.lua:100-103)
+-- log p(y | hyp): the density the slice sampler evaluates (samplers/slice.lua:100-103).
+-- X and y stay resident between evaluations: the first call fits, later calls b7_gp_refit.
 function model:log_density(hyp, X, Y)
-  local _, logml = self:fit(X, Y, hyp, B.C.B7_FIT_LOGML_ONLY)
+  local hyp = hyp:contiguous():double():view(1, -1)
+  if self._density == nil or self._density_X ~= X or self._density_Y ~= Y then
+    local gp, logml = self:fit(X, Y, hyp, B.C.B7_FIT_LOGML_ONLY)
+    self._density, self._density_X, self._density_Y = gp, X, Y
+    return logml[1]
+  end
+  local info, logml, jit = ffi.new('int[1]'), torch.DoubleTensor(1), torch.DoubleTensor(1)
+  B.check(B.C.b7_gp_refit(self._density, hyp:data(), B.C.B7_FIT_LOGML_ONLY, info, logml:data(), jit:data()), 'b7_gp_refit')
   return logml[1]
 end
 

@@ -240,6 +240,22 @@ def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
         f.free()
 
 
+def test_refit_reuses_handle(ctx, oracle):
+    # slice-sampler density path: same observations, new draws, no reallocation
+    Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 2, 1500, 1e-2)
+    f = models.GPFactors(Xo, y, hyp, flags=L.FIT_LOGML_ONLY)
+    hyp2 = hyp + 0.1
+    f.refit(hyp2, L.FIT_LOGML_ONLY)
+    ref = [oracle.gp_fit(Xo, y, h, 0)["logml"] for h in hyp2]
+    assert rel(f.logml, np.array(ref), 1e-300) <= 1e-11
+    f.refit(hyp, L.FIT_PREDICT)
+    g = models.GPFactors(Xo, y, hyp)
+    assert np.array_equal(f.logml, g.logml)
+    assert all(np.array_equal(a, b) for a, b in zip(f.predict(1, Xc), g.predict(1, Xc)))
+    f.free()
+    g.free()
+
+
 def test_argument_errors(ctx):
     X, y = np.zeros((4, 2)), np.zeros(4)
     with pytest.raises(L.B7Error, match="H must be d\\+3"):
