@@ -25,24 +25,28 @@ namespace {
 constexpr int kParStride = B7_MAX_DIMS + 4;
 constexpr double kLog2Pi = 1.83787706640934548356;
 
+// Stream-ordered allocation from the device's memory pool (release threshold = unlimited, set in
+// b7_init): buffers freed by one fit are handed back to the next without a driver round trip
+// (a fresh cudaMalloc of the 4.3 GB factor array costs tens of ms; the reference allocates and
+// garbage-collects on every call, bots/bayesopt.lua:77).
 template <typename T>
-int dev_alloc(T** p, size_t count) {
+int dev_alloc(b7_ctx* ctx, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
   if (e != cudaSuccess) {
-    b7_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    b7_set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
     return B7_ERR_NOMEM;
   }
   return 0;
 }
+inline void dev_free(b7_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 
-int grow(double** p, size_t* have, size_t need_bytes) {
+int grow(b7_ctx* ctx, double** p, size_t* have, size_t need_bytes) {
   if (*have >= need_bytes) return 0;
-  if (*p) cudaFree(*p);
+  dev_free(ctx, *p);
   *p = nullptr; *have = 0;
-  cudaError_t e = cudaMalloc((void**)p, need_bytes);
-  if (e != cudaSuccess) { b7_set_error("cudaMalloc of %zu bytes failed: %s", need_bytes, cudaGetErrorString(e)); return B7_ERR_NOMEM; }
+  B7_CHECK(dev_alloc(ctx, p, need_bytes / sizeof(double) + 1));
   *have = need_bytes;
   return 0;
 }
@@ -56,9 +60,9 @@ int sync_removed(b7_grid* g) {
   if (!g->removed_dirty) return 0;
   int64_t n = (int64_t)g->removed.size();
   if (n > g->removed_cap) {
-    if (g->removed_dev) cudaFree(g->removed_dev);
+    dev_free(g->ctx, g->removed_dev);
     g->removed_cap = std::max<int64_t>(256, 2 * n);
-    B7_CHECK(dev_alloc(&g->removed_dev, (size_t)g->removed_cap));
+    B7_CHECK(dev_alloc(g->ctx, &g->removed_dev, (size_t)g->removed_cap));
   }
   if (n > 0)
     B7_CUDA(cudaMemcpyAsync(g->removed_dev, g->removed.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, g->ctx->stream));
@@ -165,6 +169,10 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evA, cudaEventDisableTiming));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evB, cudaEventDisableTiming));
+  cudaMemPool_t pool;
+  B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
+  B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));
@@ -177,10 +185,12 @@ void b7_shutdown(b7_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->ks) cudaFree(ctx->ks);
-  if (ctx->moments) cudaFree(ctx->moments);
-  if (ctx->xs_stage) cudaFree(ctx->xs_stage);
+  dev_free(ctx, ctx->ks);
+  dev_free(ctx, ctx->moments);
+  dev_free(ctx, ctx->xs_stage);
+  cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->stream2);
+  { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   cudaStreamDestroy(ctx->stream2);
@@ -248,12 +258,12 @@ int b7_sobol_generate(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, 
   if ((mins == nullptr) != (maxes == nullptr)) { b7_set_error("sobol: one-sided rescaling is done by the host wrapper; pass both mins and maxes or neither"); return B7_ERR_ARG; }
   B7_CUDA(cudaSetDevice(ctx->device));
   double* dev = nullptr;
-  B7_CHECK(dev_alloc(&dev, (size_t)count * dims));
+  B7_CHECK(dev_alloc(ctx, &dev, (size_t)count * dims));
   double *dmin = nullptr, *dscale = nullptr;
   if (mins) {
     double h[2 * B7_MAX_DIMS];
     for (int i = 0; i < dims; ++i) { h[i] = mins[i]; h[B7_MAX_DIMS + i] = maxes[i] + (-mins[i]); }   // torch.add(maxes, -mins)
-    B7_CHECK(dev_alloc(&dmin, 2 * B7_MAX_DIMS));
+    B7_CHECK(dev_alloc(ctx, &dmin, 2 * B7_MAX_DIMS));
     dscale = dmin + B7_MAX_DIMS;
     B7_CUDA(cudaMemcpyAsync(dmin, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     B7_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -267,8 +277,8 @@ int b7_sobol_generate(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, 
   }
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (rc == 0 && e != cudaSuccess) { b7_set_error("sobol: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
-  if (dmin) cudaFree(dmin);
-  if (rc != 0 || !out_grid) { cudaFree(dev); return rc; }
+  dev_free(ctx, dmin);
+  if (rc != 0 || !out_grid) { dev_free(ctx, dev); return rc; }
   b7_grid* g = new b7_grid();
   g->ctx = ctx; g->rows = count; g->d = dims; g->X = dev;
   *out_grid = g;
@@ -280,7 +290,7 @@ int b7_grid_from_host(b7_ctx* ctx, const double* X, int64_t M, int d, b7_grid** 
   *out_grid = nullptr;
   B7_CUDA(cudaSetDevice(ctx->device));
   double* dev = nullptr;
-  B7_CHECK(dev_alloc(&dev, (size_t)M * d));
+  B7_CHECK(dev_alloc(ctx, &dev, (size_t)M * d));
   if (M > 0) {
     B7_CUDA(cudaMemcpyAsync(dev, X, (size_t)M * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     B7_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -331,8 +341,8 @@ int b7_grid_remove(b7_grid* g, int64_t compacted_index, double* removed_row) {
 void b7_grid_free(b7_grid* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
-  if (g->X) cudaFree(g->X);
-  if (g->removed_dev) cudaFree(g->removed_dev);
+  dev_free(g->ctx, g->X);
+  dev_free(g->ctx, g->removed_dev);
   delete g;
 }
 
@@ -343,7 +353,7 @@ void b7_gp_free(b7_gp* gp) {
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
   void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
-  for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* p : ptrs) dev_free(gp->ctx, p);
   for (size_t i = 0; i < g_gp_host.size(); ++i)
     if (g_gp_host[i].first == gp) { delete g_gp_host[i].second; g_gp_host.erase(g_gp_host.begin() + i); break; }
   delete gp;
@@ -422,13 +432,13 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
   // max_eps = ||src||_F of the matrix that failed
   B7_CHECK(build_kxx(gp, s, 1));
   double* rows = nullptr;
-  B7_CHECK(dev_alloc(&rows, (size_t)gp->N));
+  B7_CHECK(dev_alloc(ctx, &rows, (size_t)gp->N));
   frob_rows_kernel<<<gp->N, 256, 0, ctx->stream>>>(gp->fac + s * fs, gp->Np, gp->N, rows);
   b7_count(ctx);
   std::vector<double> rh((size_t)gp->N);
   B7_CUDA(cudaMemcpyAsync(rh.data(), rows, gp->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   B7_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(rows);
+  dev_free(ctx, rows);
   double ss = 0.0;
   for (double v : rh) ss += v;
   const double max_eps = sqrt(ss);
@@ -500,11 +510,11 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
   const size_t Np = gp->Np, fs = Np * Np, ds = (size_t)gp->NB * B7_NB * B7_NB;
   int rc = 0;
   auto fail = [&](int code) { b7_gp_free(gp); return code; };
-  if ((rc = dev_alloc(&gp->X, (size_t)N * d)) || (rc = dev_alloc(&gp->Xt, (size_t)d * Np)) || (rc = dev_alloc(&gp->y, (size_t)N)) ||
-      (rc = dev_alloc(&gp->par, (size_t)S * kParStride)) || (rc = dev_alloc(&gp->fac, (size_t)S * fs)) ||
-      (rc = dev_alloc(&gp->dinv, (size_t)S * ds)) || (rc = dev_alloc(&gp->dinvT, (size_t)S * ds)) ||
-      (rc = dev_alloc(&gp->beta, (size_t)S * Np)) || (rc = dev_alloc(&gp->tt, (size_t)S * B7_NB * Np)) ||
-      (rc = dev_alloc(&gp->logdet, (size_t)S)) || (rc = dev_alloc(&gp->info, (size_t)S)))
+  if ((rc = dev_alloc(ctx, &gp->X, (size_t)N * d)) || (rc = dev_alloc(ctx, &gp->Xt, (size_t)d * Np)) || (rc = dev_alloc(ctx, &gp->y, (size_t)N)) ||
+      (rc = dev_alloc(ctx, &gp->par, (size_t)S * kParStride)) || (rc = dev_alloc(ctx, &gp->fac, (size_t)S * fs)) ||
+      (rc = dev_alloc(ctx, &gp->dinv, (size_t)S * ds)) || (rc = dev_alloc(ctx, &gp->dinvT, (size_t)S * ds)) ||
+      (rc = dev_alloc(ctx, &gp->beta, (size_t)S * Np)) || (rc = dev_alloc(ctx, &gp->tt, (size_t)S * B7_NB * Np)) ||
+      (rc = dev_alloc(ctx, &gp->logdet, (size_t)S)) || (rc = dev_alloc(ctx, &gp->info, (size_t)S)))
     return fail(rc);
   GpHostCopy* hc = new GpHostCopy();
   hc->y.assign(y, y + N);
@@ -585,11 +595,11 @@ int b7_gp_read_factor(b7_gp* gp, int s, double* out_host) {
   if (!gp || !out_host || s < 0 || s >= gp->S) return B7_ERR_ARG;
   B7_CUDA(cudaSetDevice(gp->ctx->device));
   double* tmp = nullptr;
-  B7_CHECK(dev_alloc(&tmp, (size_t)gp->N * gp->N));
+  B7_CHECK(dev_alloc(gp->ctx, &tmp, (size_t)gp->N * gp->N));
   int rc = b7_launch_untile(gp->ctx, gp->fac + (size_t)s * gp->Np * gp->Np, tmp, gp->Np, gp->N);
   cudaError_t e = cudaMemcpyAsync(out_host, tmp, (size_t)gp->N * gp->N * 8, cudaMemcpyDeviceToHost, gp->ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(gp->ctx->stream);
-  cudaFree(tmp);
+  dev_free(gp->ctx, tmp);
   if (rc < 0) return rc;
   if (e != cudaSuccess) { b7_set_error("gp_read_factor: %s", cudaGetErrorString(e)); return B7_ERR_CUDA; }
   return 0;
@@ -599,7 +609,7 @@ int b7_gp_read_factor(b7_gp* gp, int s, double* out_host) {
 static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, double* mean, double* var) {
   b7_ctx* ctx = gp->ctx;
   const int64_t rp = pad128(rows);
-  B7_CHECK(grow(&ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
+  B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
   {
     StageTimer t(ctx, ST_KSTAR);
     B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, A, rows, rp, gp->d, gp->Xt, gp->N, gp->Np,
@@ -630,8 +640,8 @@ int b7_gp_predict(b7_gp* gp, int s, const double* Xs, int64_t M, double* mean, d
   b7_ctx* ctx = gp->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
   const int64_t P = panel_rows(ctx);
-  B7_CHECK(grow(&ctx->xs_stage, &ctx->xs_bytes, (size_t)std::min(P, pad128(M)) * gp->d * 8));
-  B7_CHECK(grow(&ctx->moments, &ctx->moments_bytes, (size_t)2 * std::min(P, pad128(M)) * 8));
+  B7_CHECK(grow(ctx, &ctx->xs_stage, &ctx->xs_bytes, (size_t)std::min(P, pad128(M)) * gp->d * 8));
+  B7_CHECK(grow(ctx, &ctx->moments, &ctx->moments_bytes, (size_t)2 * std::min(P, pad128(M)) * 8));
   for (int64_t c0 = 0; c0 < M; c0 += P) {
     const int64_t n = std::min(P, M - c0), np = pad128(n);
     B7_CUDA(cudaMemcpyAsync(ctx->xs_stage, Xs + c0 * gp->d, (size_t)n * gp->d * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -647,8 +657,10 @@ int b7_gp_predict(b7_gp* gp, int s, const double* Xs, int64_t M, double* mean, d
 /* ------------------------------------------------------------------ acquisition */
 
 struct PartBuf {
+  b7_ctx* ctx = nullptr;
   double* best = nullptr; int64_t* idx = nullptr; int64_t* nan = nullptr; int cap = 0;
-  ~PartBuf() { if (best) cudaFree(best); if (idx) cudaFree(idx); if (nan) cudaFree(nan); }
+  explicit PartBuf(b7_ctx* c) : ctx(c) {}
+  ~PartBuf() { dev_free(ctx, best); dev_free(ctx, idx); dev_free(ctx, nan); }
 };
 
 static int finish_argmax(b7_ctx* ctx, PartBuf& pb, int n_parts, double* best, int64_t* row0based, int64_t* nan_count) {
@@ -684,13 +696,13 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
   B7_CHECK(sync_removed(grid));
   const int64_t P = panel_rows(ctx), Pp = std::min(P, pad128(std::max<int64_t>(count, 1)));
   const int S = gp->S;
-  B7_CHECK(grow(&ctx->moments, &ctx->moments_bytes, (size_t)2 * S * Pp * 8));
+  B7_CHECK(grow(ctx, &ctx->moments, &ctx->moments_bytes, (size_t)2 * S * Pp * 8));
   const int64_t n_panels = (count + P - 1) / P;
-  PartBuf pb;
+  PartBuf pb(ctx);
   pb.cap = (int)(n_panels * b7_score_grid_size(ctx, P)) + 1;
-  B7_CHECK(dev_alloc(&pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.nan, (size_t)pb.cap));
+  B7_CHECK(dev_alloc(ctx, &pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.nan, (size_t)pb.cap));
   double* score_dev = nullptr;
-  if (score_host) B7_CHECK(dev_alloc(&score_dev, (size_t)std::max<int64_t>(count, 1)));
+  if (score_host) B7_CHECK(dev_alloc(ctx, &score_dev, (size_t)std::max<int64_t>(count, 1)));
   int n_parts = 0, rc = 0;
   for (int64_t c0 = 0; c0 < count && rc == 0; c0 += P) {
     const int64_t n = std::min(P, count - c0), np = pad128(n);
@@ -713,7 +725,7 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { b7_set_error("acq_score D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
   }
-  if (score_dev) cudaFree(score_dev);
+  dev_free(ctx, score_dev);
   if (rc < 0) return rc;
   if (argmax_original) *argmax_original = r0 + 1;
   if (best) *best = bv;
@@ -745,9 +757,9 @@ int b7_score_moments(b7_ctx* ctx, int kind, const double* mean, const double* va
   B7_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)S * std::max<int64_t>(M, 1);
   double *dm = nullptr, *dv = nullptr, *ds = nullptr;
-  B7_CHECK(dev_alloc(&dm, n)); B7_CHECK(dev_alloc(&dv, n)); B7_CHECK(dev_alloc(&ds, (size_t)std::max<int64_t>(M, 1)));
-  PartBuf pb; pb.cap = b7_score_grid_size(ctx, M) + 1;
-  B7_CHECK(dev_alloc(&pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(&pb.nan, (size_t)pb.cap));
+  B7_CHECK(dev_alloc(ctx, &dm, n)); B7_CHECK(dev_alloc(ctx, &dv, n)); B7_CHECK(dev_alloc(ctx, &ds, (size_t)std::max<int64_t>(M, 1)));
+  PartBuf pb(ctx); pb.cap = b7_score_grid_size(ctx, M) + 1;
+  B7_CHECK(dev_alloc(ctx, &pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.nan, (size_t)pb.cap));
   int rc = 0, parts = 0;
   if (M > 0) {
     B7_CUDA(cudaMemcpyAsync(dm, mean, (size_t)S * M * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -763,7 +775,7 @@ int b7_score_moments(b7_ctx* ctx, int kind, const double* mean, const double* va
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { b7_set_error("score_moments D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
   }
-  cudaFree(dm); cudaFree(dv); cudaFree(ds);
+  dev_free(ctx, dm); dev_free(ctx, dv); dev_free(ctx, ds);
   if (rc < 0) return rc;
   if (argmax) *argmax = r0 + 1;
   if (best) *best = bv;
