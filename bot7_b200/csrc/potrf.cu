@@ -53,6 +53,17 @@ __device__ __forceinline__ void frag_mac(double& c0, double& c1, const double* _
   }
 }
 
+// 1/sqrt(x) without the library's out-of-line slow path (its CALL forces the 16 row registers of the
+// factorisation below through local memory): float seed + three Newton steps, <= 2 ulp for normal x;
+// x <= 0 or NaN gives inf / NaN, which is what the info logic wants to see propagate.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
 // ---- diagonal block: potf2 + inverse + x_j + logdet + info -------------------------------------
 // Blocked inside shared memory so that almost all arithmetic is DMMA on 8x8 fragments:
 //   for each 16-wide sub-block: warp 0 factors the 16x16 diagonal piece in registers (shuffles) and
@@ -95,7 +106,7 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
 #pragma unroll
       for (int q = 0; q < SB; ++q) {
         const double piv = __shfl_sync(0xffffffffu, a[q], q);
-        const double inv = rsqrt(piv);
+        const double inv = rsqrt_nr(piv);
         if (lane == 0) {
           pivs[j0 + q] = piv;
           invs[j0 + q] = inv;
@@ -103,9 +114,11 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
         }
         const double my = a[q] * inv;   // L[lane][q] for lane > q
 #pragma unroll
-        for (int k = q + 1; k < SB; ++k) {
-          const double lk = __shfl_sync(0xffffffffu, my, k);
-          if (lane >= k) a[k] = fma(-my, lk, a[k]);
+        for (int k = 1; k < SB; ++k) {      // constant trip count: keeps a[] in registers
+          if (k > q) {
+            const double lk = __shfl_sync(0xffffffffu, my, k);
+            if (lane >= k) a[k] = fma(-my, lk, a[k]);
+          }
         }
         a[q] = (lane > q) ? my : (lane == q ? piv * inv : a[q]);
       }
@@ -124,7 +137,8 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
       for (int i = 0; i < SB; ++i) {
         double acc = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-        for (int k = 0; k < i; ++k) acc = fma(-LD[i * 17 + k], x[k], acc);
+        for (int k = 0; k < SB; ++k)
+          if (k < i) acc = fma(-LD[i * 17 + k], x[k], acc);
         x[i] = (i >= lane) ? acc * invs[j0 + i] : 0.0;
       }
       if (lane < SB) {
