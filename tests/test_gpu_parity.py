@@ -196,6 +196,42 @@ def test_gp_ragged_sizes_vs_oracle(ctx, oracle, N, d, S, M, noise):
     f.free()
 
 
+@pytest.mark.parametrize("kern,bound,sign,tradeoff", [(1, "upper", 1.0, 2.0), (0, "upper", -1.0, 0.5), (1, "lower", 1.0, 1.0)])
+def test_confidence_bound_variants_and_matern_at_size(ctx, oracle, kern, bound, sign, tradeoff):
+    # config 2 of BASELINE.json in miniature (UCB, single MAP draw), both kernels, every bound/sign branch
+    Xo, y, hyp, Xc = make_problem(oracle, 640, 6, 1, 9000, 1e-2, seed=kern + 5)
+    f = models.GPFactors(Xo, y, hyp, kern)
+    grid = grids.DeviceGrid.from_host(Xc)
+    sc = np.empty(Xc.shape[0])
+    am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+    L.check(L.lib().b7_acq_score(f.handle, grid.handle, L.SCORE_CB, tradeoff, L.BOUND_UPPER if bound == "upper" else L.BOUND_LOWER,
+                                 sign, float(y.min()), L.dptr(sc), C.byref(am), C.byref(amo), C.byref(best), C.byref(nn)))
+    ref = oracle.acquisition(Xo, y, hyp, Xc, kern, False, oracle.SCORE_CB, tradeoff, bound, sign)
+    assert rel(sc, ref["score"], 1e-6 * np.max(np.abs(ref["score"]))) <= 1e-7
+    assert am.value == ref["idx"] and best.value == sc[am.value - 1]
+    f.free()
+
+
+def test_empty_and_tiny_grids(ctx, oracle):
+    Xo, y, hyp, Xc = make_problem(oracle, 64, 3, 2, 5, 1e-2)
+    f = models.GPFactors(Xo, y, hyp)
+    am, amo, best, nn = C.c_int64(7), C.c_int64(7), C.c_double(), C.c_int64(7)
+    g0 = grids.DeviceGrid.from_host(np.zeros((0, 3)))
+    L.check(L.lib().b7_acq_score(f.handle, g0.handle, L.SCORE_EI, 0.0, 0, -1.0, 0.0, None, C.byref(am), C.byref(amo), C.byref(best), C.byref(nn)))
+    assert (am.value, amo.value, nn.value) == (0, 0, 0) and np.isnan(best.value)
+    g1 = grids.DeviceGrid.from_host(Xc)
+    for i in range(4):
+        g1.remove(1)                                                # only the last original row stays live
+    L.check(L.lib().b7_acq_score(f.handle, g1.handle, L.SCORE_EI, 0.0, 0, -1.0, float(y.min()), None, C.byref(am), C.byref(amo),
+                                 C.byref(best), C.byref(nn)))
+    assert (am.value, amo.value) == (1, 5)
+    g2 = grids.DeviceGrid.from_host(np.zeros((3, 4)))
+    with pytest.raises(L.B7Error, match="grid dims"):
+        L.check(L.lib().b7_acq_score(f.handle, g2.handle, L.SCORE_EI, 0.0, 0, -1.0, 0.0, None, C.byref(am), C.byref(amo),
+                                     C.byref(best), C.byref(nn)))
+    f.free()
+
+
 def test_gp_noiseless_illconditioned_reports_scaled_error(ctx, oracle):
     # sigma_n^2 = 1e-6: cond(K) ~ 1e8; two correct fp64 algorithms differ by cond*eps.  Bar: absolute
     # error scaled by the prior variance (what the subtraction sf2 - sum v^2 can resolve).
