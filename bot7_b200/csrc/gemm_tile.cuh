@@ -8,9 +8,13 @@
 //
 // Shared-memory layout ("fragment order"): a 128 x 16 operand k-tile is stored as
 // [k-group g = 0..3][row 0..127][4 doubles]; the A/B fragment of rows 8f..8f+7, k-group g is then the
-// 256 contiguous bytes at g*4096 + f*256, read by one conflict-free LDS.64 per lane.  cp.async
-// moves 16-byte pieces from the row-major global tile into that order (two lanes per row, 512
-// contiguous shared bytes per warp instruction), 4-stage pipeline, one __syncthreads per k-tile.
+// 256 contiguous bytes at g*4096 + f*256, read by one conflict-free LDS.64 per lane.
+// Two ways of filling it: (1) Ring / mainloop_bulk: the operands already are in that order in HBM
+// ("tiled layout") and one cp.async.bulk (TMA) per operand k-step lands them, mbarrier-tracked, no
+// CTA-wide barrier -- what every kernel of the path uses; (2) load_operand / mainloop: per-thread
+// cp.async of 16-byte pieces from a row-major matrix, one __syncthreads per k-tile -- the first
+// version, kept for tools/dmma_loop.cu, which shows why (1) exists (22 % of the DMMA issue slots
+// are lost to LSU contention with (2)).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
