@@ -16,6 +16,7 @@ import numpy as np
 
 from . import _lib as L
 from .samplers import slice as slice_sampler
+from .samplers import slice_speculative
 
 KERNELS = {"ardse": L.KERNEL_ARDSE, "matern52": L.KERNEL_MATERN52, "matern_52": L.KERNEL_MATERN52}
 
@@ -122,6 +123,8 @@ class gp_regressor:
         c.setdefault("nSamples", 1)
         c.setdefault("burnin", 0)
         c.setdefault("prior_std", 2.0)     # declared: independent N(0, prior_std^2) on every hyp entry
+        c.setdefault("speculative", True)  # batched density evaluations; the chain is identical either way
+        c.setdefault("spec_width", 4)
         self.config = c
         self.ctx = ctx
         self.rng = rng or np.random.default_rng(0)
@@ -157,7 +160,7 @@ class gp_regressor:
         """log p(y | h) + log p(h): one density evaluation of the slice sampler = one GP fit
         (K build + potrf + beta + logdet) with nothing but a scalar coming back."""
         h = L.as_f64(h).reshape(1, -1)
-        key = (np.asarray(X).tobytes(), np.asarray(Y).tobytes())
+        key = (np.asarray(X).tobytes(), np.asarray(Y).tobytes(), 1)
         if self._density_key != key:                 # X, y stay resident across the sampler's evaluations
             if self._density is not None:
                 self._density.free()
@@ -170,6 +173,31 @@ class gp_regressor:
         sd = self.config["prior_std"]
         return lp - 0.5 * float(np.sum((h / sd) ** 2))
 
+    def log_density_batch(self, H, X, Y):
+        """k density evaluations in one device call (one batched fit of k factors): what the speculative
+        sampler asks for.  The handle keeps `spec_width` slots; short batches repeat their last row."""
+        H = np.atleast_2d(L.as_f64(H))
+        k, W = H.shape[0], max(int(self.config["spec_width"]), 3)
+        out = []
+        for c0 in range(0, k, W):
+            chunk = H[c0:c0 + W]
+            n = chunk.shape[0]
+            padded = np.concatenate([chunk, np.repeat(chunk[-1:], W - n, 0)], 0) if n < W else chunk
+            key = (np.asarray(X).tobytes(), np.asarray(Y).tobytes(), W)
+            if self._density_key != key:
+                if self._density is not None:
+                    self._density.free()
+                self._density = GPFactors(X, Y, padded, self.config["kernel"], self.config["noiseless"], L.FIT_LOGML_ONLY, self.ctx)
+                self._density_key = key
+            else:
+                self._density.refit(padded, L.FIT_LOGML_ONLY)
+            f = self._density
+            sd = self.config["prior_std"]
+            for i in range(n):
+                lp = float(f.logml[i]) if f.info[i] == 0 and np.isfinite(f.logml[i]) else -np.inf
+                out.append(lp - 0.5 * float(np.sum((chunk[i] / sd) ** 2)))
+        return out
+
     def sample_hypers(self, X, Y, _a=None, _b=None, single=False):
         """bots/bayesopt.lua:68,74: slice-sample the hyper-parameter posterior, keep the chain state."""
         if self.hyp is None:
@@ -178,7 +206,11 @@ class gp_regressor:
         out = np.empty((n, self.hyp.size))
         x = self.hyp.reshape(1, -1).copy()
         for i in range(n):
-            x = slice_sampler()(lambda v, a: self.log_density(v, X, Y), x, {"nSamples": 1}, None, rng=self.rng)
+            if self.config["speculative"]:
+                x = slice_speculative()(lambda V, a: self.log_density_batch(V, X, Y), x, {"nSamples": 1}, None,
+                                        rng=self.rng, width=int(self.config["spec_width"]))
+            else:
+                x = slice_sampler()(lambda v, a: self.log_density(v, X, Y), x, {"nSamples": 1}, None, rng=self.rng)
             out[i] = x[0]
         self.hyp = out[-1].copy()
         return out[0] if single else out

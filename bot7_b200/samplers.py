@@ -98,3 +98,113 @@ class slice:  # noqa: A001  (name kept from the reference)
             neg = dx < 0
             left = np.where(neg, dx, left)
         return x0 + d_vec * dx
+
+
+class slice_speculative(slice):
+    """Same chain as `slice`, fewer sequential density evaluations.
+
+    The reference sampler (samplers/slice.lua:92-168) calls `f` strictly one point at a time, and for
+    GP hyper-parameters every call is a device fit whose cost at small and medium N is launch latency,
+    not arithmetic.  Here `f_batch(points[k x h]) -> k values` evaluates several points in one device
+    call (one batched fit), and the control flow asks for points *before* it knows it needs them:
+
+      * the current point, the first right and the first left bracket end (their positions depend on the
+        RNG only) go out as one batch;
+      * stepping out evaluates the next `width` ends of the side being extended at once;
+      * stepping in pre-computes the next `width` proposals under the assumption that each one is
+        rejected (the bracket update after a rejection depends only on the sign of the proposal).
+
+    Speculative results that the sequential algorithm would not have requested are discarded, and the
+    RNG is rewound to exactly the state the sequential algorithm would have left it in, so for a given
+    generator the samples are bit-identical to `slice` (tests/test_host_logic.py).
+    """
+
+    def __call__(self, f_batch, X0, opt=None, f_args=None, rng=None, width=4):
+        opt = self.configure(opt)
+        rng = rng or np.random.default_rng()
+        X0 = np.atleast_2d(np.asarray(X0, dtype=np.float64))
+        X0 = np.tile(X0.copy(), (int(opt["nSamples"]), 1))
+        N, xDim = X0.shape
+        samples = np.empty((N, xDim))
+        self.calls = 0          # device calls (batches)
+        self.evals = 0          # points evaluated, speculative ones included
+        if opt.get("gibbs"):
+            raise NotImplementedError("gibbs sweeps use the sequential sampler")
+        for n in range(N):
+            x0 = X0[n:n + 1]
+            d_vec = rng.standard_normal((1, xDim))
+            d_vec = d_vec / np.linalg.norm(d_vec)
+            samples[n] = self._directed(opt, f_batch, f_args, d_vec, x0, rng, int(width))
+        return samples
+
+    def _eval(self, f_batch, f_args, x0, d_vec, dxs):
+        pts = np.concatenate([x0 + d_vec * dx for dx in dxs], 0)
+        self.calls += 1
+        self.evals += len(dxs)
+        return [float(v) for v in f_batch(pts, f_args)]
+
+    def _directed(self, opt, f_batch, f_args, d_vec, x0, rng, width):
+        xDim = x0.shape[1]
+        stepsize = opt.get("widths")
+        if stepsize is None:
+            stepsize = np.full((1, xDim), opt.get("width") or 1.0)
+        zero = np.zeros((1, xDim))
+        # RNG order of the reference: log U (:108), then the bracket (:114)
+        logu = np.log(rng.random()) if opt["logspace"] else rng.random()
+        right = rng.random((1, xDim)) * stepsize
+        left = right - stepsize
+        f0, fr, fl = self._eval(f_batch, f_args, x0, d_vec, [zero, right, left])
+        Y = f0 + logu if opt["logspace"] else f0 * logu
+        if opt["step_out"]:
+            for side in (+1, -1):
+                end, fe, itr = (right, fr, 0) if side > 0 else (left, fl, 0)
+                cache = []
+                while fe > Y and itr < opt["max_step"]:
+                    itr += 1
+                    end = end + side * stepsize
+                    if not cache:
+                        ends, e = [], end
+                        for _ in range(width):        # repeated addition, exactly like the sequential loop
+                            ends.append(e)
+                            e = e + side * stepsize
+                        cache = list(zip(ends, self._eval(f_batch, f_args, x0, d_vec, ends)))
+                    end, fe = cache.pop(0)
+                if side > 0:
+                    right = end
+                else:
+                    left = end
+        dx = zero
+        while True:
+            # proposals under the assumption "every earlier one of this batch is rejected"
+            state = rng.bit_generator.state
+            l, r, props, states = left, right, [], []
+            for _ in range(width):
+                u = rng.random()
+                states.append(rng.bit_generator.state)
+                p = l + (r - l) * u
+                props.append((p, l, r))
+                if (p == 0.0).any():
+                    break
+                r = np.where(p > 0, p, r)
+                l = np.where(p < 0, p, l)
+            ys = self._eval(f_batch, f_args, x0, d_vec, [p for p, _, _ in props])
+            done = False
+            for (p, l_before, r_before), y, st in zip(props, ys, states):
+                dx, left, right = p, l_before, r_before
+                rng.bit_generator.state = st          # RNG exactly as after this proposal's draw
+                if y != y:
+                    print("Error: samplers.slice encountered a NaN")
+                    done = True
+                    break
+                if y > Y:
+                    done = True
+                    break
+                if (dx == 0.0).any():
+                    print("Error: samplers.slice shrank to zero")
+                    done = True
+                    break
+                right = np.where(dx > 0, dx, right)
+                left = np.where(dx < 0, dx, left)
+            if done:
+                break
+        return x0 + d_vec * dx

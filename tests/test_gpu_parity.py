@@ -445,6 +445,25 @@ def test_reference_api_predict_and_scores(ctx, oracle):
     assert rel(cb, oracle.cb_compute(mr, vr), 1e-6) <= 1e-7
 
 
+def test_speculative_hyper_sampling_gives_the_same_experiment(ctx, oracle):
+    # batched density evaluations (one fit of 4 factors per device call) vs one factor per call: the factors
+    # are computed independently per draw with a fixed order, so the chains and the nominations coincide
+    import time
+    hypers = [{"name": "x%d" % i, "size": 1, "min": 0.0, "max": 1.0} for i in range(2)]
+    runs, walls = [], []
+    for spec in (True, False):
+        cfg = {"bot": {"budget": 9, "nInitial": 3, "nSamples": 3, "verbose": 0}, "grid": {"size": 3000},
+               "model": {"speculative": spec}}
+        bot = bots.bayesopt(lambda x: oracle.braninhoo(x)[0], hypers, cfg, rng=np.random.default_rng(11))
+        t0 = time.perf_counter()
+        bot.run_experiment()
+        walls.append(time.perf_counter() - t0)
+        runs.append((bot.observed.copy(), bot.responses.copy(), bot.model.hyp.copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2])
+    print("bayesopt 9 trials: speculative %.2f s, sequential %.2f s" % tuple(walls))
+
+
 def test_bayesopt_loop_branin(ctx, oracle):
     # config 1 of BASELINE.json in miniature: Branin-Hoo 2D, EI, Sobol grid, fixed hyper draws
     hypers = [{"name": "x1", "size": 1, "min": 0.0, "max": 1.0}, {"name": "x2", "size": 1, "min": 0.0, "max": 1.0}]

@@ -87,6 +87,32 @@ def test_slice_sampler_control_flow():
     assert g.shape == (3, 2)
 
 
+def test_speculative_sampler_reproduces_the_sequential_chain():
+    # batched / speculative density evaluations must not change a single bit of the chain nor the RNG state
+    def f(x, _):
+        return float(-0.5 * np.sum(((x - 1.0) / np.array([0.5, 2.0, 0.1])) ** 2))
+
+    def fb(X, _):
+        return [f(X[i:i + 1], None) for i in range(X.shape[0])]
+
+    for seed, opt in ((0, {}), (1, {"width": 0.37}), (2, {"step_out": False}), (3, {"widths": np.array([[0.3, 2.5, 0.05]])})):
+        r1, r2 = np.random.default_rng(seed), np.random.default_rng(seed)
+        x1 = x2 = np.zeros((1, 3))
+        seq_evals, calls = [0], 0
+
+        def fc(x, a):
+            seq_evals[0] += 1
+            return f(x, a)
+        sp = samplers.slice_speculative()
+        for _ in range(40):
+            x1 = samplers.slice()(fc, x1, dict(opt), None, rng=r1)
+            x2 = sp(fb, x2, dict(opt), None, rng=r2, width=4)
+            calls += sp.calls
+            assert np.array_equal(x1, x2)
+        assert r1.random() == r2.random()
+        assert calls < 0.7 * seq_evals[0]            # fewer sequential device calls
+
+
 def test_slice_sampler_nan_guard(capsys):
     s = samplers.slice()
     out = s(lambda x, a: float("nan") if abs(x[0, 0]) > 0 else 0.0, np.zeros((1, 1)), {"step_out": False}, None,
