@@ -120,6 +120,11 @@ def cpu_scoring_sample(n_draws, m_cand, reps=1):
     (seconds per draw for m_cand candidates, fit seconds per draw, cores)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import b7_oracle as o
+    try:    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     X = o.sobol_points(DIMS, N_OBS + m_cand)
     Xo, Xc = X[:N_OBS], X[N_OBS:]
     y = o.hartmann6(Xo)

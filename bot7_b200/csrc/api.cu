@@ -76,10 +76,15 @@ __device__ __forceinline__ long long tiled_index(int Np, int row, int k) {
 }
 
 __global__ void frob_rows_kernel(const double* __restrict__ A, int Np, int N, double* __restrict__ out) {
-  // sum of squares of row blockIdx.x (first N columns), fixed-order tree
+  // sum of squares of row blockIdx.x of the symmetric matrix, read from its lower triangle only
+  // (the upper blocks are never built): 2 * strictly-lower + diagonal; fixed-order tree
   __shared__ double sh[256];
   double s = 0.0;
-  for (int k = threadIdx.x; k < N; k += blockDim.x) { const double v = A[tiled_index(Np, blockIdx.x, k)]; s += v * v; }
+  const int row = blockIdx.x;
+  for (int k = threadIdx.x; k <= row; k += blockDim.x) {
+    const double v = A[tiled_index(Np, row, k)];
+    s += (k < row ? 2.0 : 1.0) * v * v;
+  }
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {

@@ -29,6 +29,8 @@ cov_kernel(const double* __restrict__ A, long long rows, long long rows_pad, int
   double* out = out_base + (long long)blockIdx.z * out_stride;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * kRowsPerBlock;
+  // K(X,X): only 128x128 blocks at or below the diagonal are ever read (lower Cholesky)
+  if (is_kxx && (long long)(blockIdx.x * blockDim.x) > (r0 | 127)) return;
   for (int e = threadIdx.x; e < kRowsPerBlock * DT; e += blockDim.x) {
     int r = e / DT, i = e % DT;
     long long row = r0 + r;

@@ -85,6 +85,31 @@ __device__ __forceinline__ void compute_stage(const double* __restrict__ sA, con
   }
 }
 
+// Same for a k-tile that lies inside the diagonal 128x128 block of a lower-triangular A: rows 8f..8f+7 of the
+// tile are zero right of column 8f+7, so the fragment products with k0 > row_max are skipped (the predicates
+// depend on warp, fragment and k only: no divergence).  k_rel = column offset of the tile inside the block.
+__device__ __forceinline__ void compute_stage_tri(const double* __restrict__ sA, const double* __restrict__ sB, int wm,
+                                                  int wn, int lane, Acc& acc, int k_rel) {
+#pragma unroll
+  for (int g4 = 0; g4 < KG; ++g4) {
+    const int k0 = k_rel + 4 * g4;
+    if (k0 > 64 * wm + 63) continue;          // whole warp tile is zero from here on
+    double b[4];
+    const double* pa = sA + g4 * (BM * 4) + (64 * wm) * 4 + lane;
+    const double* pb = sB + g4 * (BN * 4) + (32 * wn) * 4 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = pb[j * 32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (k0 <= 64 * wm + 8 * i + 7) {
+        const double a = pa[i * 32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc.c[i][j][0], acc.c[i][j][1], a, b[j]);
+      }
+    }
+  }
+}
+
 // acc += A[0:128, 0:16*KT] * B[0:128, 0:16*KT]^T  (gA, gB point at the first k column)
 __device__ __forceinline__ void mainloop(const double* __restrict__ gA, long long lda, const double* __restrict__ gB,
                                          long long ldb, int KT, double* smem, Acc& acc) {

@@ -84,7 +84,8 @@ posterior_kernel(const double* __restrict__ LinvT, const double* __restrict__ be
     const int slot = (int)(it % P_STAGES);
     mbar_wait(full + slot, (unsigned)((it / P_STAGES) & 1));
     const double* st = smem + slot * 2 * TILE_DOUBLES;
-    compute_stage(st, st + TILE_DOUBLES, wm, wn, lane, acc);
+    if (c_kt >= c_rb * KPB) compute_stage_tri(st, st + TILE_DOUBLES, wm, wn, lane, acc, (c_kt - c_rb * KPB) * TILE_K);
+    else compute_stage(st, st + TILE_DOUBLES, wm, wn, lane, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + slot);
     if (++c_kt == (c_rb + 1) * KPB) {
