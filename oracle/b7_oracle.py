@@ -326,9 +326,9 @@ def argmax_first(score):
     nan_count = int(nan.sum())
     if score.size == 0 or nan_count == score.size:
         return float("nan"), 0, nan_count
-    masked = np.where(nan, -np.inf, score)
-    idx = int(np.argmax(masked))            # numpy argmax returns the first maximum
-    return float(masked[idx]), idx + 1, nan_count
+    valid = np.flatnonzero(~nan)
+    idx = int(valid[np.argmax(score[valid])])   # numpy argmax returns the first maximum among the non-NaN entries
+    return float(score[idx]), idx + 1, nan_count
 
 
 # --------------------------------------------------------------------------------------------
