@@ -130,6 +130,14 @@ int factor(b7_gp* gp, int s0, int count) {
 
 }  // namespace
 
+int b7_pool_alloc(b7_ctx* ctx, void** p, size_t bytes) {
+  char* q = nullptr;
+  int rc = dev_alloc(ctx, &q, bytes);
+  *p = q;
+  return rc;
+}
+void b7_pool_free(b7_ctx* ctx, void* p) { dev_free(ctx, p); }
+
 struct GpHostCopy { std::vector<double> y; };
 static std::vector<std::pair<b7_gp*, GpHostCopy*>> g_gp_host;   // y kept on the host for the retry path
 

@@ -91,6 +91,10 @@ struct b7_blr {
   std::vector<double> par_host;
 };
 
+// stream-ordered pool allocation on the context stream (api.cu)
+int b7_pool_alloc(b7_ctx* ctx, void** p, size_t bytes);
+void b7_pool_free(b7_ctx* ctx, void* p);
+
 // ---- launch bookkeeping ----
 static inline void b7_count(b7_ctx* ctx, int n = 1) { ctx->launches += n; }
 // Brackets the launches of one stage with CUDA events on the context stream (only when profiling

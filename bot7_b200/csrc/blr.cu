@@ -226,30 +226,146 @@ int launch_moments(b7_ctx* ctx, const double* Z, int64_t M, const b7_blr* blr, i
   }
 }
 
-template <typename T>
-int dalloc(T** p, size_t n) {
-  *p = nullptr;
-  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
-  if (e != cudaSuccess) { b7_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return B7_ERR_NOMEM; }
+// ---- DNGO basis: X -> features through the trained ReLU MLP (models/dngo.lua:155-171) ------------------
+// One dense layer: out[c][j] = act(b[j] + sum_k W[j][k] in[c][k]).  One thread per candidate keeps its input row in
+// registers (width rounded up to a multiple of 8, <= 64); the weights sit transposed in shared memory so that the
+// four outputs computed together read 32 contiguous bytes per k (two LDS.128 warp broadcasts per 4 FMAs); input and
+// output tiles are staged through shared memory so that global accesses are coalesced.
+template <int HP>
+__global__ void __launch_bounds__(128)
+mlp_layer_kernel(const double* __restrict__ in, long long M, int h_in, int h_out, const double* __restrict__ W,
+                 const double* __restrict__ bias, int relu, double* __restrict__ out) {
+  extern __shared__ __align__(16) double sh[];
+  const int ho4 = (h_out + 3) & ~3;
+  double* Wt = sh;                          // [HP][ho4]  (Wt[k][j] = W[j][k], zero padded)
+  double* bs = Wt + HP * ho4;               // [ho4]
+  double* tile = bs + ho4;                  // 128 x max(h_in | 1, h_out | 1)
+  const int ldi = h_in | 1, ldo = h_out | 1, tid = threadIdx.x;
+  const long long c0 = (long long)blockIdx.x * 128;
+  const int nc = (int)min((long long)128, M - c0);
+  for (int e = tid; e < HP * ho4; e += 128) {
+    const int k = e / ho4, j = e % ho4;
+    Wt[e] = (k < h_in && j < h_out) ? W[(long long)j * h_in + k] : 0.0;
+  }
+  for (int e = tid; e < ho4; e += 128) bs[e] = e < h_out ? bias[e] : 0.0;
+  for (int e = tid; e < nc * h_in; e += 128) tile[(e / h_in) * ldi + e % h_in] = in[c0 * h_in + e];
+  __syncthreads();
+  double x[HP];
+#pragma unroll
+  for (int k = 0; k < HP; ++k) x[k] = (k < h_in && tid < nc) ? tile[tid * ldi + k] : 0.0;
+  __syncthreads();   // the tile is reused for the outputs
+  for (int j = 0; j < ho4; j += 4) {
+    double a0 = bs[j], a1 = bs[j + 1], a2 = bs[j + 2], a3 = bs[j + 3];
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+      const double2 w01 = *reinterpret_cast<const double2*>(Wt + k * ho4 + j);
+      const double2 w23 = *reinterpret_cast<const double2*>(Wt + k * ho4 + j + 2);
+      a0 = fma(w01.x, x[k], a0);
+      a1 = fma(w01.y, x[k], a1);
+      a2 = fma(w23.x, x[k], a2);
+      a3 = fma(w23.y, x[k], a3);
+    }
+    if (relu) { a0 = a0 > 0.0 ? a0 : 0.0; a1 = a1 > 0.0 ? a1 : 0.0; a2 = a2 > 0.0 ? a2 : 0.0; a3 = a3 > 0.0 ? a3 : 0.0; }
+    if (j < h_out) tile[tid * ldo + j] = a0;
+    if (j + 1 < h_out) tile[tid * ldo + j + 1] = a1;
+    if (j + 2 < h_out) tile[tid * ldo + j + 2] = a2;
+    if (j + 3 < h_out) tile[tid * ldo + j + 3] = a3;
+  }
+  __syncthreads();
+  for (int e = tid; e < nc * h_out; e += 128) out[c0 * h_out + e] = tile[(e / h_out) * ldo + e % h_out];
+}
+
+template <int HP>
+int launch_mlp_layer(b7_ctx* ctx, const double* in, int64_t M, int h_in, int h_out, const double* W, const double* b, int relu,
+                     double* out) {
+  const int ho4 = (h_out + 3) & ~3, wmax = (h_in | 1) > (h_out | 1) ? (h_in | 1) : (h_out | 1);
+  const size_t smem = ((size_t)HP * ho4 + ho4 + 128 * (size_t)wmax) * 8;
+  static bool done = false;
+  if (!done) { B7_CUDA(cudaFuncSetAttribute(mlp_layer_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+  mlp_layer_kernel<HP><<<(unsigned)((M + 127) / 128), 128, smem, ctx->stream>>>(in, M, h_in, h_out, W, b, relu, out);
+  b7_count(ctx);
+  B7_CUDA(cudaGetLastError());
   return 0;
 }
 
+template <typename T>
+int dalloc(b7_ctx* ctx, T** p, size_t n) {
+  void* q = nullptr;
+  int rc = b7_pool_alloc(ctx, &q, std::max<size_t>(n, 1) * sizeof(T));
+  *p = static_cast<T*>(q);
+  return rc;
+}
+
 struct Part {
+  b7_ctx* ctx;
   double* best = nullptr; int64_t* idx = nullptr; int64_t* nan = nullptr;
-  ~Part() { if (best) cudaFree(best); if (idx) cudaFree(idx); if (nan) cudaFree(nan); }
+  explicit Part(b7_ctx* c) : ctx(c) {}
+  ~Part() { b7_pool_free(ctx, best); b7_pool_free(ctx, idx); b7_pool_free(ctx, nan); }
 };
 
 }  // namespace
 
 extern "C" {
 
+int b7_mlp_features(b7_ctx* ctx, b7_grid* in, int n_layers, const int* dims, const double* const* W, const double* const* b,
+                    int relu_last, b7_grid** out) {
+  if (!ctx || !in || !out || n_layers < 1 || !dims || !W || !b || dims[0] != in->d) {
+    b7_set_error("mlp_features: bad arguments (dims[0] must equal the grid's dims)");
+    return B7_ERR_ARG;
+  }
+  *out = nullptr;
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] < 1 || dims[l] > 64) { b7_set_error("mlp_features: layer widths must be in [1, 64] (got %d)", dims[l]); return B7_ERR_ARG; }
+  B7_CUDA(cudaSetDevice(ctx->device));
+  const int64_t M = in->rows;
+  const double* cur = in->X;
+  double* bufs[2] = {nullptr, nullptr};
+  int rc = 0;
+  StageTimer t(ctx, ST_BLR);
+  for (int l = 0; l < n_layers && rc == 0; ++l) {
+    const int hi = dims[l], ho = dims[l + 1];
+    double *dW = nullptr, *db = nullptr, *dst = nullptr;
+    if ((rc = dalloc(ctx, &dW, (size_t)hi * ho)) || (rc = dalloc(ctx, &db, (size_t)ho)) || (rc = dalloc(ctx, &dst, (size_t)std::max<int64_t>(M, 1) * ho))) break;
+    cudaMemcpyAsync(dW, W[l], (size_t)hi * ho * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(db, b[l], (size_t)ho * 8, cudaMemcpyHostToDevice, ctx->stream);
+    const int relu = (l < n_layers - 1) || relu_last;
+    if (M > 0) {
+      switch ((hi + 7) / 8) {
+        case 1: rc = launch_mlp_layer<8>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 2: rc = launch_mlp_layer<16>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 3: rc = launch_mlp_layer<24>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 4: rc = launch_mlp_layer<32>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 5: rc = launch_mlp_layer<40>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 6: rc = launch_mlp_layer<48>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        case 7: rc = launch_mlp_layer<56>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+        default: rc = launch_mlp_layer<64>(ctx, cur, M, hi, ho, dW, db, relu, dst); break;
+      }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    b7_pool_free(ctx, dW); b7_pool_free(ctx, db);
+    if (bufs[l & 1]) b7_pool_free(ctx, bufs[l & 1]);
+    bufs[l & 1] = dst;
+    cur = dst;
+  }
+  t.stop(n_layers);
+  const int last = (n_layers - 1) & 1;
+  if (bufs[last ^ 1]) b7_pool_free(ctx, bufs[last ^ 1]);
+  if (rc < 0) { if (bufs[last]) b7_pool_free(ctx, bufs[last]); return rc; }
+  b7_grid* g = new b7_grid();
+  g->ctx = ctx; g->rows = M; g->d = dims[n_layers]; g->X = bufs[last];
+  g->removed = in->removed;            // the feature grid inherits the candidate bookkeeping
+  g->removed_dirty = !g->removed.empty();
+  *out = g;
+  return 0;
+}
+
 void b7_blr_free(b7_blr* blr) {
   if (!blr) return;
   cudaSetDevice(blr->ctx->device);
   cudaStreamSynchronize(blr->ctx->stream);
-  if (blr->Linv) cudaFree(blr->Linv);
-  if (blr->w) cudaFree(blr->w);
-  if (blr->par) cudaFree(blr->par);
+  b7_pool_free(blr->ctx, blr->Linv);
+  b7_pool_free(blr->ctx, blr->w);
+  b7_pool_free(blr->ctx, blr->par);
   delete blr;
 }
 
@@ -268,10 +384,10 @@ int b7_blr_fit(b7_ctx* ctx, const double* Z0, const double* y, int N, int D, con
   const int n_out = D * D + 2 * D;
   const int blocks = std::min(kGramBlocks, (N + 31) / 32);
   int rc = 0;
-  if ((rc = dalloc(&dZ, (size_t)N * D)) || (rc = dalloc(&dy, (size_t)N)) || (rc = dalloc(&partial, (size_t)blocks * n_out)) ||
-      (rc = dalloc(&dinfo, (size_t)S)) || (rc = dalloc(&blr->Linv, (size_t)S * D * D)) || (rc = dalloc(&blr->w, (size_t)S * D)) ||
-      (rc = dalloc(&blr->par, (size_t)S * 4))) {
-    b7_blr_free(blr); cudaFree(dZ); cudaFree(dy); cudaFree(partial); cudaFree(dinfo);
+  if ((rc = dalloc(ctx, &dZ, (size_t)N * D)) || (rc = dalloc(ctx, &dy, (size_t)N)) || (rc = dalloc(ctx, &partial, (size_t)blocks * n_out)) ||
+      (rc = dalloc(ctx, &dinfo, (size_t)S)) || (rc = dalloc(ctx, &blr->Linv, (size_t)S * D * D)) || (rc = dalloc(ctx, &blr->w, (size_t)S * D)) ||
+      (rc = dalloc(ctx, &blr->par, (size_t)S * 4))) {
+    b7_blr_free(blr); b7_pool_free(ctx, dZ); b7_pool_free(ctx, dy); b7_pool_free(ctx, partial); b7_pool_free(ctx, dinfo);
     return rc;
   }
   blr->par_host.resize((size_t)S * 4);
@@ -298,7 +414,7 @@ int b7_blr_fit(b7_ctx* ctx, const double* Z0, const double* y, int N, int D, con
   cudaMemcpyAsync(hi.data(), dinfo, S * sizeof(int), cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
-  cudaFree(dZ); cudaFree(dy); cudaFree(partial); cudaFree(dinfo);
+  b7_pool_free(ctx, dZ); b7_pool_free(ctx, dy); b7_pool_free(ctx, partial); b7_pool_free(ctx, dinfo);
   if (e != cudaSuccess) { b7_set_error("blr_fit: %s", cudaGetErrorString(e)); b7_blr_free(blr); return B7_ERR_CUDA; }
   int worst = 0;
   for (int s = 0; s < S; ++s) { if (info) info[s] = hi[s]; if (hi[s] && !worst) worst = hi[s]; }
@@ -312,8 +428,8 @@ int b7_blr_predict(b7_blr* blr, int s, const double* Z1, int64_t M, double* mean
   B7_CUDA(cudaSetDevice(ctx->device));
   const int64_t chunk = 1 << 20;
   double *dz = nullptr, *dm = nullptr;
-  B7_CHECK(dalloc(&dz, (size_t)std::min(chunk, std::max<int64_t>(M, 1)) * blr->D));
-  B7_CHECK(dalloc(&dm, (size_t)2 * std::min(chunk, std::max<int64_t>(M, 1))));
+  B7_CHECK(dalloc(ctx, &dz, (size_t)std::min(chunk, std::max<int64_t>(M, 1)) * blr->D));
+  B7_CHECK(dalloc(ctx, &dm, (size_t)2 * std::min(chunk, std::max<int64_t>(M, 1))));
   int rc = 0;
   for (int64_t c0 = 0; c0 < M && rc == 0; c0 += chunk) {
     const int64_t n = std::min(chunk, M - c0);
@@ -326,7 +442,7 @@ int b7_blr_predict(b7_blr* blr, int s, const double* Z1, int64_t M, double* mean
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == 0 && e != cudaSuccess) { b7_set_error("blr_predict: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
   }
-  cudaFree(dz); cudaFree(dm);
+  b7_pool_free(ctx, dz); b7_pool_free(ctx, dm);
   return rc;
 }
 
@@ -341,17 +457,17 @@ int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int 
   const int64_t M = features->rows;
   const int S = blr->S;
   double *mom = nullptr, *sc = nullptr;
-  B7_CHECK(dalloc(&mom, (size_t)2 * S * std::max<int64_t>(M, 1)));
-  B7_CHECK(dalloc(&sc, (size_t)std::max<int64_t>(M, 1)));
-  Part pb;
+  B7_CHECK(dalloc(ctx, &mom, (size_t)2 * S * std::max<int64_t>(M, 1)));
+  B7_CHECK(dalloc(ctx, &sc, (size_t)std::max<int64_t>(M, 1)));
+  Part pb(ctx);
   const int cap = b7_score_grid_size(ctx, M) + 1;
-  B7_CHECK(dalloc(&pb.best, (size_t)cap)); B7_CHECK(dalloc(&pb.idx, (size_t)cap)); B7_CHECK(dalloc(&pb.nan, (size_t)cap));
+  B7_CHECK(dalloc(ctx, &pb.best, (size_t)cap)); B7_CHECK(dalloc(ctx, &pb.idx, (size_t)cap)); B7_CHECK(dalloc(ctx, &pb.nan, (size_t)cap));
   if (features->removed_dirty || features->removed.size()) {
     int64_t n = (int64_t)features->removed.size();
     if (n > features->removed_cap) {
-      if (features->removed_dev) cudaFree(features->removed_dev);
+      b7_pool_free(ctx, features->removed_dev);
       features->removed_cap = std::max<int64_t>(256, 2 * n);
-      B7_CHECK(dalloc(&features->removed_dev, (size_t)features->removed_cap));
+      B7_CHECK(dalloc(ctx, &features->removed_dev, (size_t)features->removed_cap));
     }
     if (n) cudaMemcpyAsync(features->removed_dev, features->removed.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream);
     features->removed_dirty = false;
@@ -376,7 +492,7 @@ int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int 
   }
   if (rc == 0 && score_host && M > 0) cudaMemcpyAsync(score_host, sc, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(mom); cudaFree(sc);
+  b7_pool_free(ctx, mom); b7_pool_free(ctx, sc);
   if (rc == 0 && e != cudaSuccess) { b7_set_error("blr_score: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
   if (rc < 0) return rc;
   double bv = -INFINITY; int64_t bi = INT64_MAX, nn = 0;

@@ -281,6 +281,23 @@ class BLRFactors:
             pass
 
 
+def mlp_features(grid, weights, biases, relu_last=True, ctx=None):
+    """DNGO basis on the device (models/dngo.lua:164-171 without the 32-row minibatch loop and without
+    the host round trip of Z1): ReLU MLP forward of a DeviceGrid, returns a DeviceGrid of features.
+    weights[l]: (h_out x h_in) like torch nn.Linear.weight; biases[l]: (h_out,)."""
+    from .grids import DeviceGrid
+    ctx = ctx or grid.ctx
+    Ws = [L.as_f64(w) for w in weights]
+    bs = [L.as_f64(b).reshape(-1) for b in biases]
+    n = len(Ws)
+    dims = (C.c_int * (n + 1))(*([Ws[0].shape[1]] + [w.shape[0] for w in Ws]))
+    Wp = (C.POINTER(C.c_double) * n)(*[L.dptr(w) for w in Ws])
+    bp = (C.POINTER(C.c_double) * n)(*[L.dptr(b) for b in bs])
+    out = C.c_void_p()
+    L.check(L.lib().b7_mlp_features(ctx.handle, grid.handle, n, dims, Wp, bp, int(bool(relu_last)), C.byref(out)), "b7_mlp_features")
+    return DeviceGrid(out, ctx)
+
+
 class bayes_linear:
     """gp.models.bayes_linear as used by models/dngo.lua:77-79,174:
     predict(Z0, Y0, Z1, nil, hyp, req) with hyp == 'marginalize' or a S x 3 array."""

@@ -132,6 +132,13 @@ int b7_score_moments(b7_ctx* ctx, int kind, const double* mean, const double* va
 
 /* ---- DNGO head: replaces bayes_linear:predict called from models/dngo.lua:174 -----------------
  * hyp: S x 3 rows [log alpha_p, log beta, m] (oracle/SPEC.md). */
+/* DNGO basis functions (models/dngo.lua:155-171: X -> output of the last hidden layer of the trained network):
+ * ReLU MLP forward in fp64 on a device-resident grid.  dims[0..n_layers] are the widths (dims[0] = grid dims, each
+ * <= 64), W[l] is dims[l+1] x dims[l] row-major (torch nn.Linear.weight), b[l] has dims[l+1] entries; every layer is
+ * followed by ReLU (the last one only if relu_last).  The result is a new device grid of features that inherits the
+ * removed rows of the input grid and feeds b7_blr_score. */
+int b7_mlp_features(b7_ctx* ctx, b7_grid* in, int n_layers, const int* dims, const double* const* W,
+                    const double* const* b, int relu_last, b7_grid** out);
 int b7_blr_fit(b7_ctx* ctx, const double* Z0, const double* y, int N, int D, const double* hyp, int S,
                b7_blr** out, int* info);
 int b7_blr_predict(b7_blr* blr, int s, const double* Z1, int64_t M, double* mean, double* var);

@@ -462,6 +462,18 @@ def blr_predict(fit, Z1):
     return mean, var
 
 
+def mlp_features(X, weights, biases, relu_last=True):
+    """DNGO basis (models/dngo.lua:155-171): output of the last hidden layer of a Linear/ReLU stack
+    (nnTools/builder.lua:133-159).  nn.Linear computes x W^T + b through BLAS (summation order unspecified),
+    nn.ReLU is max(0, x): parity is to rounding, not bit-exact."""
+    Z = np.asarray(X, dtype=np.float64)
+    for l, (W, b) in enumerate(zip(weights, biases)):
+        Z = Z @ np.asarray(W, dtype=np.float64).T + np.asarray(b, dtype=np.float64).reshape(1, -1)
+        if l < len(weights) - 1 or relu_last:
+            Z = np.maximum(Z, 0.0)
+    return Z
+
+
 # --------------------------------------------------------------------------------------------
 # acquisition over a grid, marginalised over draws (PINNED control flow: bots/bayesopt.lua:56-99)
 # --------------------------------------------------------------------------------------------

@@ -427,6 +427,48 @@ def test_blr_shapes_vs_oracle(ctx, oracle, N, D):
         models.BLRFactors(np.zeros((10, 65)), np.zeros(10), hyp)
 
 
+def test_dngo_device_pipeline(ctx, oracle):
+    # config 4 of BASELINE.json in miniature, entirely on the device: Sobol grid -> MLP basis -> BLR moments
+    # -> EI -> argmax, with a removed candidate carried from the input grid to the feature grid
+    r = np.random.default_rng(21)
+    d, h, N, M = 6, 50, 400, 30000
+    Ws = [r.normal(size=(h, d)) / np.sqrt(d), r.normal(size=(h, h)) / np.sqrt(h), r.normal(size=(h, h)) / np.sqrt(h)]
+    bs = [0.1 * r.normal(size=h) for _ in range(3)]
+    sob = grids.sobol({"size": N + M, "dims": d})
+    Xo = sob.generate({"size": N, "dims": d})
+    y = oracle.hartmann6(Xo)
+    y = (y - y.mean()) / y.std()
+    grid = sob.generate_device(first=N, count=M)
+    grid.remove(123)
+    feats = models.mlp_features(grid, Ws, bs)
+    Xc = grid.read()
+    Zref = oracle.mlp_features(Xc, Ws, bs)
+    Z = feats.read()
+    assert Z.shape == (M, h) and np.max(np.abs(Z - Zref)) <= 1e-12 * max(1.0, np.max(np.abs(Zref)))
+    Z0 = oracle.mlp_features(Xo, Ws, bs)
+    hyp = np.array([[0.0, np.log(1e2), 0.0], [np.log(2.0), np.log(30.0), 0.1]])
+    f = models.BLRFactors(Z0, y, hyp)
+    sc = np.empty(M)
+    am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+    fmin = float(y.min())
+    L.check(L.lib().b7_blr_score(f.handle, feats.handle, L.SCORE_EI, 0.0, 0, -1.0, fmin, L.dptr(sc), C.byref(am), C.byref(amo),
+                                 C.byref(best), C.byref(nn)))
+    per = []
+    for s in range(2):
+        mr, vr = oracle.blr_predict(oracle.blr_fit(Z0, y, hyp[s]), Zref)
+        per.append(oracle.ei_compute(mr, vr, fmin, 0.0))
+    ref = oracle.mc_average(per)
+    assert np.isnan(sc[122])                                        # removed row travels with the grid
+    live = np.ones(M, dtype=bool)
+    live[122] = False
+    assert rel(sc[live], ref[live], 1e-6 * ref[live].max()) <= 1e-7
+    b, i, n = oracle.argmax_first(np.where(live, ref, np.nan))
+    assert amo.value == i and am.value == i - (1 if i > 123 else 0)
+    with pytest.raises(L.B7Error, match="widths"):
+        models.mlp_features(grid, [r.normal(size=(65, d))], [np.zeros(65)])
+    f.free()
+
+
 # ---------------------------------------------------------------------------------- the reference-facing API end to end
 
 def test_reference_api_predict_and_scores(ctx, oracle):

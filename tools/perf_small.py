@@ -39,4 +39,13 @@ for rep in range(3):
     L.check(lib.b7_blr_score(h, g, 0, 0.0, 0, -1.0, float(y.min()), None, C.byref(am), C.byref(amo), C.byref(b), C.byref(nn)))
     st = ctx.stage_times(); best = min(best, st["blr"][0])
 out[f"blr_score_D50_M{Mb}"] = {"ms": best, "GBps": Mb * (8 * D + 16) / best * 1e-6, "TFLOPs": Mb * (D * D + 2 * D) / best * 1e-9, "cand_per_s": Mb / best * 1e3, "score_ms": st["score"][0]}
+# DNGO basis on the device: 6 -> 50 -> 50 -> 50 ReLU MLP over 2^22 Sobol candidates (config 4 end to end on the GPU)
+from bot7_b200 import grids, models
+sob = grids.sobol({"size": Mb, "dims": 6}); gx = sob.generate_device()
+Ws = [r.normal(size=(50, 6)), r.normal(size=(50, 50)) / 7, r.normal(size=(50, 50)) / 7]; bs = [np.zeros(50)] * 3
+best = 1e9
+for rep in range(3):
+    ctx.reset_timers(); fz = models.mlp_features(gx, Ws, bs); best = min(best, ctx.stage_times()["blr"][0]); fz.free()
+macs = Mb * (6 * 50 + 2 * 50 * 50)
+out[f"dngo_mlp_6_50_50_50_M{Mb}"] = {"ms": best, "TFLOPs": 2 * macs / best * 1e-9, "cand_per_s": Mb / best * 1e3}
 print(json.dumps(out, indent=1))
