@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bot7_b200 import _lib as L
-lib = L.lib(); ctx = L.Context(0); ctx.set_profiling(True)
+lib = L.lib(); ctx = L.Context.default(0); ctx.set_profiling(True)
 out = {}
 # Sobol: config 5 shape slice (d=20) and d=6, device resident
 for d, M in ((6, 1 << 24), (20, 1 << 24)):
