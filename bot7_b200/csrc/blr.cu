@@ -198,10 +198,10 @@ int launch_moments_dp(b7_ctx* ctx, const double* Z, int64_t M, int D, const b7_b
                       double* mean, double* var) {
   const size_t a = ((size_t)DP * DP + DP) * 8, b = 128 * (size_t)(D | 1) * 8;
   const size_t smem = a > b ? a : b;
-  static bool done = false;
-  if (!done) {
+  static bool done[16] = {false};   // function attributes are per device
+  if (!done[ctx->device & 15]) {
     B7_CUDA(cudaFuncSetAttribute(blr_moments_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    done = true;
+    done[ctx->device & 15] = true;
   }
   blr_moments_kernel<DP><<<(unsigned)((M + 127) / 128), 128, smem, ctx->stream>>>(
       Z, M, D, blr->Linv + (size_t)s0 * D * D, blr->w + (size_t)s0 * D, blr->par + (size_t)s0 * 4, S, ld_out, mean, var);
@@ -280,8 +280,11 @@ int launch_mlp_layer(b7_ctx* ctx, const double* in, int64_t M, int h_in, int h_o
                      double* out) {
   const int ho4 = (h_out + 3) & ~3, wmax = (h_in | 1) > (h_out | 1) ? (h_in | 1) : (h_out | 1);
   const size_t smem = ((size_t)HP * ho4 + ho4 + 128 * (size_t)wmax) * 8;
-  static bool done = false;
-  if (!done) { B7_CUDA(cudaFuncSetAttribute(mlp_layer_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+  static bool done[16] = {false};
+  if (!done[ctx->device & 15]) {
+    B7_CUDA(cudaFuncSetAttribute(mlp_layer_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    done[ctx->device & 15] = true;
+  }
   mlp_layer_kernel<HP><<<(unsigned)((M + 127) / 128), 128, smem, ctx->stream>>>(in, M, h_in, h_out, W, b, relu, out);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
@@ -400,7 +403,8 @@ int b7_blr_fit(b7_ctx* ctx, const double* Z0, const double* y, int N, int D, con
   cudaMemcpyAsync(dZ, Z0, (size_t)N * D * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(blr->par, blr->par_host.data(), (size_t)S * 4 * 8, cudaMemcpyHostToDevice, st);
-  static bool attr_done = false;
+  static bool attr_done_dev[16] = {false};
+  bool& attr_done = attr_done_dev[ctx->device & 15];
   if (!attr_done) {
     cudaFuncSetAttribute(blr_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kMaxD * (kMaxD + 1) + 2 * kMaxD) * 8);
     attr_done = true;

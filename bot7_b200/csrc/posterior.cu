@@ -138,15 +138,15 @@ posterior_kernel(const double* __restrict__ LinvT, const double* __restrict__ be
   }
 }
 
-bool g_attr = false;
+bool g_attr[16] = {false};   // function attributes are per device
 
 }  // namespace
 
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT, const double* beta, int Np, const double* ksT,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var) {
-  if (!g_attr) {
+  if (!g_attr[ctx->device & 15]) {
     B7_CUDA(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    g_attr = true;
+    g_attr[ctx->device & 15] = true;
   }
   if (cols_pad <= 0) return 0;
   posterior_kernel<<<(unsigned)(cols_pad / BN), P_THREADS, P_SMEM, ctx->stream>>>(LinvT, beta, Np, Np / B7_NB, ksT, sf2,

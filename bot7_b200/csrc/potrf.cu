@@ -369,15 +369,15 @@ __global__ void untile_kernel(const double* __restrict__ facT, double* __restric
   for (int k = threadIdx.x; k < N; k += blockDim.x) out[(long long)row * N + k] = src[elem_off(row & 127, k)];
 }
 
-bool g_attr_done = false;
-int set_attrs() {
-  if (g_attr_done) return 0;
+bool g_attr_done[16] = {false};   // function attributes are per device
+int set_attrs(int device) {
+  if (g_attr_done[device & 15]) return 0;
   B7_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
   B7_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   B7_CUDA(cudaFuncSetAttribute(trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   B7_CUDA(cudaFuncSetAttribute(inv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   B7_CUDA(cudaFuncSetAttribute(inv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
-  g_attr_done = true;
+  g_attr_done[device & 15] = true;
   return 0;
 }
 
@@ -385,7 +385,7 @@ int set_attrs() {
 
 int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
-  B7_CHECK(set_attrs());
+  B7_CHECK(set_attrs(ctx->device));
   const int Np = gp->Np, NB = gp->NB;
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK;
   static const int W_env = getenv("B7_POTRF_W") ? atoi(getenv("B7_POTRF_W")) : 0;
@@ -440,7 +440,7 @@ int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out, int Np, int N
 
 int b7_launch_trtri(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
-  B7_CHECK(set_attrs());
+  B7_CHECK(set_attrs(ctx->device));
   const int Np = gp->Np, NB = gp->NB;
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK, ts = (long long)NBK * Np;
   place_diag_kernel<<<dim3(NB, count), 256, 0, ctx->stream>>>(gp->fac, fs, Np, gp->dinv, ds, s0);

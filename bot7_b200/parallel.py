@@ -65,23 +65,31 @@ class _DevBuf:
                                          "version": 3, "strides": None}
 
 
-def allgather_factors(factors, S, world, rank, group=None):
-    """After each rank factorised + inverted its draw range: all-gather L^-1 (S x Np x Np) and beta
-    (S x Np) in place on the library's device buffers."""
-    import torch
+def allgather_draws(full, per_draw, S, world, rank, group=None):
+    """In-place all-gather of a flat per-draw buffer: rank r owns draws draw_range(S, world, r) of `full`
+    (S * per_draw elements) and receives everybody else's.  Works on CPU (gloo) and CUDA (NCCL) tensors."""
     import torch.distributed as dist
+    chunks = []
+    for r in range(world):
+        s0, cnt = draw_range(S, world, r)
+        chunks.append(full[s0 * per_draw:(s0 + cnt) * per_draw])
+    if all(c.numel() == chunks[0].numel() for c in chunks):
+        dist.all_gather(chunks, chunks[rank].clone(), group=group)
+    else:                                   # S not divisible by the world size: one broadcast per owner
+        for r in range(world):
+            if chunks[r].numel():
+                dist.broadcast(chunks[r], src=r, group=group)
+    return full
+
+
+def allgather_factors(factors, S, world, rank, group=None):
+    """After each rank factorised + inverted its draw range: all-gather L^-1 (S x Np x Np, tiled layout) and
+    beta (S x Np) in place on the library's own device buffers (NCCL over NVLink)."""
+    import torch
     Np = factors.padded_n()
     for what, per_draw in ((0, Np * Np), (1, Np)):
         ptr, nbytes = factors.device_ptr(what)
         full = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
-        chunks = []
-        for r in range(world):
-            s0, cnt = draw_range(S, world, r)
-            chunks.append(full[s0 * per_draw:(s0 + cnt) * per_draw])
         torch.cuda.synchronize()
-        if all(c.numel() == chunks[0].numel() for c in chunks):
-            dist.all_gather(chunks, chunks[rank].clone(), group=group)
-        else:
-            for r in range(world):
-                dist.broadcast(chunks[r], src=r, group=group)
+        allgather_draws(full, per_draw, S, world, rank, group)
         torch.cuda.synchronize()

@@ -292,6 +292,24 @@ def test_refit_reuses_handle(ctx, oracle):
     g.free()
 
 
+def test_second_device_in_the_same_process(ctx, oracle):
+    # the Lua host is one process that may drive several GPUs: contexts are per device
+    if L.lib().b7_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx1 = L.Context(1)
+    Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 2, 3000, 1e-2)
+    f0 = models.GPFactors(Xo, y, hyp, ctx=ctx)
+    f1 = models.GPFactors(Xo, y, hyp, ctx=ctx1)
+    assert np.array_equal(f0.logml, f1.logml)
+    assert all(np.array_equal(a, b) for a, b in zip(f0.predict(1, Xc), f1.predict(1, Xc)))
+    out = np.empty((1000, 5))
+    L.check(L.lib().b7_sobol_generate(ctx1.handle, 5, 1, 1000, None, None, L.dptr(out), None))
+    assert np.array_equal(out, oracle.sobol_points(5, 1000))
+    f0.free()
+    f1.free()
+    ctx1.close()
+
+
 def test_argument_errors(ctx):
     X, y = np.zeros((4, 2)), np.zeros(4)
     with pytest.raises(L.B7Error, match="H must be d\\+3"):

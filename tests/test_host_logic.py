@@ -49,6 +49,41 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from bot7_b200 import parallel as par
+    ok = True
+    for S, per_draw in ((4, 6), (5, 3), (1, 4)):          # even split, uneven split, fewer draws than ranks
+        full = torch.full((S * per_draw,), -1.0, dtype=torch.float64)
+        s0, cnt = par.draw_range(S, world, rank)
+        for s in range(s0, s0 + cnt):                     # "factorise" my draws
+            full[s * per_draw:(s + 1) * per_draw] = torch.arange(per_draw, dtype=torch.float64) + 100.0 * s
+        par.allgather_draws(full, per_draw, S, world, rank)
+        want = torch.cat([torch.arange(per_draw, dtype=torch.float64) + 100.0 * s for s in range(S)])
+        ok = ok and bool(torch.equal(full, want))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_draw_sharded_allgather_two_gloo_ranks():
+    # the fit exchange of the multi-GPU path (each rank factorises S/G draws, then all-gathers them in place)
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctxm.Process(target=_gloo_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == {0: True, 1: True}
+
+
 def test_allgather_argmax_two_gloo_ranks():
     import torch.multiprocessing as mp
     ctxm = mp.get_context("spawn")
