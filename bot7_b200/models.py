@@ -124,7 +124,7 @@ class gp_regressor:
         c.setdefault("burnin", 0)
         c.setdefault("prior_std", 2.0)     # declared: independent N(0, prior_std^2) on every hyp entry
         c.setdefault("speculative", True)  # batched density evaluations; the chain is identical either way
-        c.setdefault("spec_width", 4)
+        c.setdefault("spec_width", 8)     # profiles/refit_vs_width_r01.json: 8 evaluations cost 1.0-2.1x one
         self.config = c
         self.ctx = ctx
         self.rng = rng or np.random.default_rng(0)

@@ -143,6 +143,21 @@ class slice_speculative(slice):
         self.evals += len(dxs)
         return [float(v) for v in f_batch(pts, f_args)]
 
+    def _propose(self, rng, left, right, width):
+        """`width` shrink proposals under the assumption that each earlier one is rejected; records the RNG state
+        after every draw so that the caller can rewind to exactly where the sequential algorithm would be."""
+        l, r, props, states = left, right, [], []
+        for _ in range(width):
+            u = rng.random()
+            states.append(rng.bit_generator.state)
+            p = l + (r - l) * u
+            props.append((p, l, r))
+            if (p == 0.0).any():
+                break
+            r = np.where(p > 0, p, r)
+            l = np.where(p < 0, p, l)
+        return props, states
+
     def _directed(self, opt, f_batch, f_args, d_vec, x0, rng, width):
         xDim = x0.shape[1]
         stepsize = opt.get("widths")
@@ -153,9 +168,18 @@ class slice_speculative(slice):
         logu = np.log(rng.random()) if opt["logspace"] else rng.random()
         right = rng.random((1, xDim)) * stepsize
         left = right - stepsize
-        f0, fr, fl = self._eval(f_batch, f_args, x0, d_vec, [zero, right, left])
+        # first device call: the point itself, both bracket ends, and -- betting that no stepping out will be
+        # needed -- the first shrink proposals for this bracket (stepping out draws no random numbers, so the
+        # proposals are the ones the sequential algorithm would make if the bet holds)
+        state0 = rng.bit_generator.state
+        props, states = self._propose(rng, left, right, max(width - 3, 1))
+        vals = self._eval(f_batch, f_args, x0, d_vec, [zero, right, left] + [p for p, _, _ in props])
+        f0, fr, fl, ys = vals[0], vals[1], vals[2], vals[3:]
         Y = f0 + logu if opt["logspace"] else f0 * logu
-        if opt["step_out"]:
+        pending = (props, states, ys)
+        if opt["step_out"] and (fr > Y or fl > Y):
+            pending = None                           # bet lost: discard the proposals, rewind the RNG
+            rng.bit_generator.state = state0
             for side in (+1, -1):
                 end, fe, itr = (right, fr, 0) if side > 0 else (left, fl, 0)
                 cache = []
@@ -175,19 +199,12 @@ class slice_speculative(slice):
                     left = end
         dx = zero
         while True:
-            # proposals under the assumption "every earlier one of this batch is rejected"
-            state = rng.bit_generator.state
-            l, r, props, states = left, right, [], []
-            for _ in range(width):
-                u = rng.random()
-                states.append(rng.bit_generator.state)
-                p = l + (r - l) * u
-                props.append((p, l, r))
-                if (p == 0.0).any():
-                    break
-                r = np.where(p > 0, p, r)
-                l = np.where(p < 0, p, l)
-            ys = self._eval(f_batch, f_args, x0, d_vec, [p for p, _, _ in props])
+            if pending is not None:
+                props, states, ys = pending
+                pending = None
+            else:
+                props, states = self._propose(rng, left, right, width)
+                ys = self._eval(f_batch, f_args, x0, d_vec, [p for p, _, _ in props])
             done = False
             for (p, l_before, r_before), y, st in zip(props, ys, states):
                 dx, left, right = p, l_before, r_before
