@@ -138,13 +138,6 @@ int b7_pool_alloc(b7_ctx* ctx, void** p, size_t bytes) {
 }
 void b7_pool_free(b7_ctx* ctx, void* p) { dev_free(ctx, p); }
 
-struct GpHostCopy { std::vector<double> y; };
-static std::vector<std::pair<b7_gp*, GpHostCopy*>> g_gp_host;   // y kept on the host for the retry path
-
-static GpHostCopy* host_copy(b7_gp* gp) {
-  for (auto& p : g_gp_host) if (p.first == gp) return p.second;
-  return nullptr;
-}
 
 extern "C" {
 
@@ -367,8 +360,6 @@ void b7_gp_free(b7_gp* gp) {
   cudaStreamSynchronize(gp->ctx->stream);
   void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
   for (void* p : ptrs) dev_free(gp->ctx, p);
-  for (size_t i = 0; i < g_gp_host.size(); ++i)
-    if (g_gp_host[i].first == gp) { delete g_gp_host[i].second; g_gp_host.erase(g_gp_host.begin() + i); break; }
   delete gp;
 }
 
@@ -438,7 +429,6 @@ int b7_gp_fit_range(b7_gp* gp, int s0, int count, int* info, double* logml, doub
 // utils.math.chol retry policy (utils/math.lua:168-216) for one draw whose plain factorisation failed
 static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
   b7_ctx* ctx = gp->ctx;
-  GpHostCopy* hc = host_copy(gp);
   const size_t fs = (size_t)gp->Np * gp->Np;
   double* par_s = gp->par + (size_t)s * kParStride;
   const double diag0 = gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS + 1];
@@ -462,7 +452,7 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
       // chol(I): L = I, beta = r, logdet = 0
       identity_kernel<<<(unsigned)((fs + 255) / 256), 256, 0, ctx->stream>>>(gp->fac + s * fs, gp->Np);
       b7_count(ctx);
-      B7_CHECK(upload_residual(gp, s, hc->y));
+      B7_CHECK(upload_residual(gp, s, gp->y_host));
       B7_CHECK(factor(gp, s, 1));
       gp->jitter[s] = INFINITY;
       gp->info_host[s] = first_info;
@@ -473,7 +463,7 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
     B7_CUDA(cudaMemcpyAsync(par_s + B7_MAX_DIMS + 1, &d, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     B7_CUDA(cudaStreamSynchronize(ctx->stream));
     B7_CHECK(build_kxx(gp, s, 1));
-    B7_CHECK(upload_residual(gp, s, hc->y));
+    B7_CHECK(upload_residual(gp, s, gp->y_host));
     B7_CHECK(factor(gp, s, 1));
     int inf = 0;
     B7_CUDA(cudaMemcpyAsync(&inf, gp->info + s, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,14 +519,12 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
       (rc = dev_alloc(ctx, &gp->beta, (size_t)S * Np)) || (rc = dev_alloc(ctx, &gp->tt, (size_t)S * B7_NB * Np)) ||
       (rc = dev_alloc(ctx, &gp->logdet, (size_t)S)) || (rc = dev_alloc(ctx, &gp->info, (size_t)S)))
     return fail(rc);
-  GpHostCopy* hc = new GpHostCopy();
-  hc->y.assign(y, y + N);
-  g_gp_host.push_back({gp, hc});
+  gp->y_host.assign(y, y + N);
   set_hypers_host(gp, hyp);
   std::vector<double> xt((size_t)d * Np, 0.0), r;
   for (int i = 0; i < N; ++i)
     for (int k = 0; k < d; ++k) xt[(size_t)k * Np + i] = X[(size_t)i * d + k];
-  residuals_host(gp, hc->y, r);
+  residuals_host(gp, gp->y_host, r);
   cudaStream_t st = ctx->stream;
   cudaError_t e;
   if ((e = cudaMemcpyAsync(gp->X, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
@@ -567,10 +555,9 @@ int b7_gp_refit(b7_gp* gp, const double* hyp, int flags, int* info, double* logm
   if (!gp || !hyp || (flags != B7_FIT_PREDICT && flags != B7_FIT_LOGML_ONLY)) { b7_set_error("gp_refit: bad arguments"); return B7_ERR_ARG; }
   b7_ctx* ctx = gp->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
-  GpHostCopy* hc = host_copy(gp);
   set_hypers_host(gp, hyp);
   std::vector<double> r;
-  residuals_host(gp, hc->y, r);
+  residuals_host(gp, gp->y_host, r);
   gp->ready = false; gp->inverted = false;
   B7_CUDA(cudaMemcpyAsync(gp->par, gp->par_host.data(), gp->par_host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   B7_CUDA(cudaMemcpyAsync(gp->beta, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -70,6 +70,7 @@ struct b7_gp {
   double* y = nullptr;      // device N
   double* par = nullptr;    // device S x (B7_MAX_DIMS + 4): w[0..39], sf2, diag_add, m, sn2
   std::vector<double> par_host;
+  std::vector<double> y_host;   // observations kept on the host for the residual upload of refits / retries
   double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1, lower, in the tiled (fragment-order) layout
   double* dinv = nullptr;   // device S x NB x (128 x 128 tiled) : inverse of the diagonal blocks of L
   double* dinvT = nullptr;  // device, transposes of dinv (tiled)
