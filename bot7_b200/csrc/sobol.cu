@@ -131,8 +131,10 @@ int b7_launch_sobol(b7_ctx* ctx, int dims, int64_t first_seed, int64_t count, co
   long long first_tile = first_seed >> kLowBits;
   long long last_tile = (first_seed + count - 1) >> kLowBits;
   long long n_tiles = last_tile - first_tile + 1;
+  // balanced: every block gets the same number of tiles (a 150 us kernel cannot afford a ragged last wave)
   long long want = (long long)ctx->sm_count * 8;
-  int grid = (int)(n_tiles < want ? n_tiles : want);
+  long long per = (n_tiles + want - 1) / want;
+  int grid = (int)((n_tiles + per - 1) / per);
   sobol_kernel<<<grid, 256, 0, ctx->stream>>>(out_dev, dims, first_seed, count, mins_dev, scale_dev,
                                               mins_dev != nullptr, first_tile, n_tiles);
   b7_count(ctx);
