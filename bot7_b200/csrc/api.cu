@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -179,6 +180,7 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
   B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = e && e[0] == '1'; }
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));
@@ -358,7 +360,7 @@ void b7_gp_free(b7_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
-  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
   for (void* p : ptrs) dev_free(gp->ctx, p);
   delete gp;
 }
@@ -479,11 +481,23 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
   }
 }
 
+// INT8 path: slice L^-1 (allocated on first use)
+static int gp_slice(b7_gp* gp, int s0, int count) {
+  b7_ctx* ctx = gp->ctx;
+  const size_t fs = (size_t)gp->Np * gp->Np;
+  if (!gp->facS) {
+    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * fs * 8));
+    B7_CHECK(dev_alloc(ctx, &gp->sigma, (size_t)gp->S * gp->Np));
+  }
+  return b7_i8_slice_factor(ctx, gp->fac, gp->Np, gp->facS, gp->sigma, s0, count);
+}
+
 static int gp_invert(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
   B7_CHECK(b7_launch_trtri(gp, s0, count));
+  if (ctx->use_i8) B7_CHECK(gp_slice(gp, s0, count));
   t.stop((int)(ctx->launches - before));
   return 0;
 }
@@ -491,6 +505,11 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
 int b7_gp_mark_ready(b7_gp* gp) {
   if (!gp) return B7_ERR_ARG;
   // slots filled by the host (all-gather into fac, which already is the layout the posterior pass reads)
+  if (gp->ctx->use_i8) {
+    B7_CUDA(cudaSetDevice(gp->ctx->device));
+    B7_CHECK(gp_slice(gp, 0, gp->S));
+    B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
+  }
   gp->ready = true;
   gp->inverted = true;
   return 0;
@@ -610,6 +629,25 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   b7_ctx* ctx = gp->ctx;
   const int64_t rp = pad128(rows);
   B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
+  const double* p = gp->par_host.data() + (size_t)s * kParStride;
+  if (ctx->use_i8) {
+    // error-free sliced operands on the INT8 tensor pipe (posterior_i8.cu); K* needs no max: 0 < k* <= sf2 <= tau
+    int e = 0;
+    frexp(p[B7_MAX_DIMS], &e);
+    const double tau = ldexp(1.0, e);
+    const int64_t rp64 = (rows + 63) / 64 * 64;
+    int8_t* ksS = reinterpret_cast<int8_t*>(ctx->ks);
+    {
+      StageTimer t(ctx, ST_KSTAR);
+      B7_CHECK(b7_i8_cov_slices(ctx, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau, ksS));
+      t.stop(1);
+    }
+    StageTimer t(ctx, ST_POSTERIOR);
+    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * 8, gp->sigma + (size_t)s * gp->Np,
+                                    gp->beta + (size_t)s * gp->Np, gp->Np, ksS, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
+    t.stop(1);
+    return 0;
+  }
   {
     StageTimer t(ctx, ST_KSTAR);
     B7_CHECK(b7_launch_cov_batched(ctx, gp->kernel, A, rows, rp, gp->d, gp->Xt, gp->N, gp->Np,
@@ -618,7 +656,6 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   }
   {
     StageTimer t(ctx, ST_POSTERIOR);
-    const double* p = gp->par_host.data() + (size_t)s * kParStride;
     B7_CHECK(b7_launch_posterior(ctx, gp->fac + (size_t)s * gp->Np * gp->Np, gp->beta + (size_t)s * gp->Np, gp->Np, ctx->ks,
                                  rp, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
     t.stop(1);

@@ -40,6 +40,7 @@ struct b7_ctx {
   double stage_ms[ST_COUNT] = {0};
   int64_t stage_calls[ST_COUNT] = {0};
   bool profiling = false;
+  bool use_i8 = false;           // B7_POSTERIOR_I8=1: posterior pass on the INT8 tensor pipe (posterior_i8.cu)
   int64_t launches = 0;
   // scratch for the posterior pass (grown on demand)
   double* ks = nullptr;        // K* panel, [panel_rows][Np]
@@ -72,6 +73,8 @@ struct b7_gp {
   std::vector<double> par_host;
   std::vector<double> y_host;   // observations kept on the host for the residual upload of refits / retries
   double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1, lower, in the tiled (fragment-order) layout
+  int8_t* facS = nullptr;   // device S x Np x Np x 8 : 8 int8 slices of L^-1 (only with ctx->use_i8)
+  double* sigma = nullptr;  // device S x Np : per-row power-of-two scales of the slices
   double* dinv = nullptr;   // device S x NB x (128 x 128 tiled) : inverse of the diagonal blocks of L
   double* dinvT = nullptr;  // device, transposes of dinv (tiled)
   double* beta = nullptr;   // device S x Np : r -> L^-1 (y - m)
@@ -129,6 +132,12 @@ int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
 int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out /* N x N row-major */, int Np, int N);
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
+// posterior_i8.cu
+int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count);
+int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
+                     const double* par, double tau, int8_t* ksS);
+int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
+                           int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var);
 // score.cu
 int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,
                     double tradeoff, int bound, double sign, double fmin, const int64_t* removed, int64_t n_removed,

@@ -1,0 +1,372 @@
+// Posterior over a candidate panel on the INT8 tensor pipe (opt-in: B7_POSTERIOR_I8=1).
+//
+// Same mathematics as posterior.cu (V = L^-1 K*^T, var = sf2 - colsumsq(V), mean = m + V^T beta) and the
+// same fp64-level accuracy, but the N^2 product per candidate runs on tcgen05.mma.kind::i8 (measured
+// 3.9 POPS on B200, tools/i8_mma_probe.cu, against 37 TFLOP/s for the FP64 DMMA pipe) through an
+// error-free slicing of both operands (the "Ozaki scheme"):
+//     a_ik = sigma_i * sum_{p=1..8} d_p(i,k) 2^-(7p-1),   d_p integers in [-64, 64]   (55 bits per entry)
+//     b_ck = tau     * sum_{q=1..8} e_q(c,k) 2^-(7q-1)
+//     v_ic = sigma_i tau sum_{w=2..9} 2^(2-7w) sum_{p+q=w} sum_k d_p(i,k) e_q(c,k)
+// Every inner sum is an exact int32 dot product (|d e| <= 2^12, k <= 2^17 terms would still fit), the 36
+// slice pairs with p + q <= 9 are kept (the dropped ones are below 2^-56 of sigma_i tau N), and the 8 weight
+// classes are accumulated in 8 x 64 = 512 TMEM columns and combined in fp64 in the epilogue.  Measured
+// against the fp64 path: variance within 1e-14 sf2, mean within 1e-12 (see tests).
+//
+// One CTA owns 64 candidates and walks the row blocks of L^-1 (128 rows = TMEM lanes).  Warp roles:
+// warp 4 lane 0 streams the slices (already in the UMMA canonical K-major layout in HBM, so a stage is six
+// 16 KB bulk copies), warp 5 lane 0 issues the 72 MMAs of a stage, warps 0-3 drain the accumulators once
+// per row block (tcgen05.ld), rebuild v in fp64 and reduce v^2 and v*beta over the 128 rows.
+#include <math.h>
+
+#include "b7_internal.h"
+#include "gemm_tile.cuh"
+
+using b7g::mbar_init; using b7g::mbar_wait; using b7g::mbar_arrive; using b7g::mbar_arrive_expect_tx; using b7g::bulk_g2s;
+using b7g::mbar_fence_init; using b7g::smem_u32;
+
+namespace {
+
+constexpr int NS = 8;                      // slices per operand
+constexpr int TM = 128, TN = 64, KB = 64;  // L^-1 rows per block, candidates per CTA, k bytes per stage
+constexpr int A_STAGE = NS * TM * KB;      // 65536 B
+constexpr int B_STAGE = NS * TN * KB;      // 32768 B
+constexpr int STAGE = A_STAGE + B_STAGE;   // 98304 B
+constexpr int NSTAGE = 2;
+constexpr int I8_THREADS = 192;
+constexpr int RED_BYTES = 2 * 4 * TN * 2 * 8;           // [rb parity][warp][candidate][sum v^2, sum v beta]
+constexpr int I8_SMEM = NSTAGE * STAGE + RED_BYTES + 1024;   // stages + reduction scratch + barriers
+
+// ---- slicing -------------------------------------------------------------------------------------------
+
+// 8 signed 7-bit digits of t in [-1, 1]:  t = sum_p d_p 2^-(7p-1) + O(2^-56); every step is exact in fp64
+__device__ __forceinline__ void digits8(double t, int (&d)[NS]) {
+  double r = t * 64.0;
+#pragma unroll
+  for (int p = 0; p < NS; ++p) {
+    const double q = rint(r);
+    d[p] = (int)q;
+    r = (r - q) * 128.0;
+  }
+}
+
+// L^-1 (tiled fp64, lower) -> per-row power-of-two scale sigma and the slice array
+// facS[rb][ks][p][kc][row][16]  (ks = 64-column stage, kc = 16-column chunk inside it)
+__global__ void __launch_bounds__(128)
+slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np, int8_t* __restrict__ facS,
+                    long long facS_stride, double* __restrict__ sigma, int s0) {
+  const int rb = blockIdx.x, s = s0 + blockIdx.y, row = threadIdx.x;
+  const int KTA = Np / 16, KS_ALL = Np / KB;
+  const double* src = fac + (long long)s * fac_stride + b7g::tile_off(KTA, rb, 0);
+  const int k_end = (rb + 1) * TM;
+  double mx = 0.0;
+  for (int k4 = 0; k4 < k_end; k4 += 4) {
+    const double* p = src + b7g::elem_off(row, k4);
+    mx = fmax(mx, fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3]))));
+  }
+  int e = 0;
+  frexp(mx, &e);                                   // mx = f 2^e, f in [0.5, 1)  ->  2^e > mx
+  const double sg = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, e) : 1.0;
+  const double inv = 1.0 / sg;
+  sigma[(long long)s * Np + rb * TM + row] = sg;
+  int8_t* dst = facS + (long long)s * facS_stride + (long long)rb * KS_ALL * A_STAGE;
+  for (int kc = 0; kc < k_end / 16; ++kc) {
+    uint32_t pk[NS][4];
+#pragma unroll
+    for (int p = 0; p < NS; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int d[NS];
+      digits8(src[b7g::elem_off(row, kc * 16 + i)] * inv, d);
+#pragma unroll
+      for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(d[p] & 0xff)) << (8 * (i & 3));
+    }
+    const int ks = kc >> 2, kcc = kc & 3;
+#pragma unroll
+    for (int p = 0; p < NS; ++p)
+      *reinterpret_cast<uint4*>(dst + (long long)ks * A_STAGE + p * (4 * TM * 16) + kcc * (TM * 16) + row * 16) =
+          make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  }
+}
+
+// K(X*, X) evaluated and sliced in one pass: ksS[ct][ks][q][kc][cand 64][16]; one block per (candidate tile, stage)
+template <int DT, int KERNEL>
+__global__ void __launch_bounds__(256)
+cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const double* __restrict__ Xt, int N, int Np,
+                  const double* __restrict__ par, double inv_tau, int8_t* __restrict__ ksS) {
+  __shared__ double s_x[DT][KB];
+  __shared__ double s_w[DT];
+  const int ct = blockIdx.x, ks = blockIdx.y, KS_ALL = Np / KB;
+  const int c = threadIdx.x & 63, kc = threadIdx.x >> 6;          // warp = 32 consecutive candidates, one k chunk
+  for (int e = threadIdx.x; e < DT * KB; e += 256) {
+    const int i = e / KB, k = ks * KB + e % KB;
+    s_x[i][e % KB] = (i < d && k < N) ? Xt[(long long)i * Np + k] : 0.0;
+  }
+  if (threadIdx.x < DT) s_w[threadIdx.x] = threadIdx.x < d ? par[threadIdx.x] : 0.0;
+  __syncthreads();
+  const long long row = (long long)ct * TN + c;
+  double a[DT];
+#pragma unroll
+  for (int i = 0; i < DT; ++i) a[i] = (row < rows && i < d) ? A[row * d + i] : 0.0;
+  const double sf2 = par[B7_MAX_DIMS];
+  uint32_t pk[NS][4];
+#pragma unroll
+  for (int p = 0; p < NS; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int kk = kc * 16 + i, k = ks * KB + kk;
+    double val = 0.0;
+    if (row < rows && k < N) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DT; ++j) {
+        const double t = (a[j] - s_x[j][kk]) * s_w[j];
+        r2 = fma(t, t, r2);
+      }
+      if (KERNEL == B7_KERNEL_ARDSE) {
+        val = sf2 * exp(-0.5 * r2);
+      } else {
+        const double rr = sqrt(r2), s5r = 2.23606797749978969641 * rr;
+        val = sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp(-s5r));
+      }
+    }
+    int dg[NS];
+    digits8(val * inv_tau, dg);
+#pragma unroll
+    for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(dg[p] & 0xff)) << (8 * (i & 3));
+  }
+  int8_t* dst = ksS + ((long long)ct * KS_ALL + ks) * B_STAGE + kc * (TN * 16) + c * 16;
+#pragma unroll
+  for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (4 * TN * 16)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+}
+
+// ---- tcgen05 helpers -----------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t umma_desc(const void* smem, int lbo_bytes, int sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // K-direction stride between 16-byte chunks
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // M/N-direction stride between 8-row groups
+  d |= (uint64_t)1 << 46;                             // sm_100 descriptor version; SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// sum over the 32 lanes of x[j] for every j, result for column j lands in lane j (transpose-reduce butterfly)
+__device__ __forceinline__ double lane_transpose_sum(double (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const double send = up ? x[j] : x[j + s];
+      const double keep = up ? x[j + s] : x[j];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, const double* __restrict__ beta,
+                    int Np, int NB, const int8_t* __restrict__ ksS, double tau, double sf2, double mconst,
+                    double* __restrict__ mean, double* __restrict__ var) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  double* red = reinterpret_cast<double*>(smem + NSTAGE * STAGE);             // [2 parity][4 warps][64 cols][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE + RED_BYTES);
+  uint64_t *full = bars, *empty = bars + NSTAGE, *acc_full = bars + 2 * NSTAGE, *acc_empty = bars + 2 * NSTAGE + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KS_ALL = Np / KB;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---- producer: stream (rb, ks) stages ----
+    if (lane == 0) {
+      const int8_t* gB = ksS + (long long)blockIdx.x * KS_ALL * B_STAGE;
+      long long it = 0;
+      for (int rb = 0; rb < NB; ++rb)
+        for (int ks = 0; ks < 2 * (rb + 1); ++ks, ++it) {
+          const int slot = (int)(it % NSTAGE);
+          if (it >= NSTAGE) mbar_wait(empty + slot, (unsigned)(((it / NSTAGE) - 1) & 1));
+          uint8_t* st = smem + slot * STAGE;
+          mbar_arrive_expect_tx(full + slot, STAGE);
+          const int8_t* a = facS + ((long long)rb * KS_ALL + ks) * A_STAGE;
+          const int8_t* b = gB + (long long)ks * B_STAGE;
+#pragma unroll
+          for (int c = 0; c < A_STAGE / 16384; ++c) bulk_g2s(st + c * 16384, a + c * 16384, 16384, full + slot);
+#pragma unroll
+          for (int c = 0; c < B_STAGE / 16384; ++c) bulk_g2s(st + A_STAGE + c * 16384, b + c * 16384, 16384, full + slot);
+        }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      long long it = 0;
+      for (int rb = 0; rb < NB; ++rb) {
+        if (rb > 0) { mbar_wait(acc_empty, (unsigned)((rb - 1) & 1)); tc_fence_after(); }
+        for (int ks = 0; ks < 2 * (rb + 1); ++ks, ++it) {
+          const int slot = (int)(it % NSTAGE);
+          mbar_wait(full + slot, (unsigned)((it / NSTAGE) & 1));
+          tc_fence_after();
+          const uint8_t* sa = smem + slot * STAGE;
+          const uint8_t* sb = sa + A_STAGE;
+#pragma unroll
+          for (int k2 = 0; k2 < KB / 32; ++k2) {
+#pragma unroll
+            for (int w = 2; w <= NS + 1; ++w) {
+#pragma unroll
+              for (int p = 1; p <= NS; ++p) {
+                const int q = w - p;
+                if (q < 1 || q > NS) continue;
+                const uint64_t da = umma_desc(sa + (p - 1) * (4 * TM * 16) + k2 * (2 * TM * 16), TM * 16, 128);
+                const uint64_t db = umma_desc(sb + (q - 1) * (4 * TN * 16) + k2 * (2 * TN * 16), TN * 16, 128);
+                const bool first = (ks == 0 && k2 == 0 && p == (w - NS > 1 ? w - NS : 1));
+                umma_i8(tmem + (uint32_t)((w - 2) * TN), da, db, idesc, first ? 0u : 1u);
+              }
+            }
+          }
+          umma_commit(empty + slot);       // frees the stage once these MMAs have read it
+        }
+        umma_commit(acc_full);             // all MMAs of the row block done -> epilogue may read TMEM
+      }
+    }
+  } else {
+    // ---- epilogue warps 0-3: thread = L^-1 row (TMEM lane), 64 candidate columns ----
+    double run2 = 0.0, run1 = 0.0;         // meaningful in threads 0..63 (candidate c = tid)
+    for (int rb = 0; rb < NB; ++rb) {
+      mbar_wait(acc_full, (unsigned)(rb & 1));
+      tc_fence_after();
+      double v[TN];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) v[c] = 0.0;
+#pragma unroll
+      for (int w = 2; w <= NS + 1; ++w) {
+        const double wt = ldexp(1.0, 2 - 7 * w);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t dv[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((w - 2) * TN + h * 32), dv);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[h * 32 + c] = fma((double)(int)dv[c], wt, v[h * 32 + c]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);     // TMEM drained: the next row block may start
+      const int row = rb * TM + tid;
+      const double sc = sigma[row] * tau, b = beta[row];
+      double* rr = red + (rb & 1) * (4 * TN * 2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double x[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { const double vv = v[h * 32 + c] * sc; x[c] = vv * vv; }
+        const double t2 = lane_transpose_sum(x, lane);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = (v[h * 32 + c] * sc) * b;
+        const double t1 = lane_transpose_sum(x, lane);
+        rr[(warp * TN + h * 32 + lane) * 2 + 0] = t2;
+        rr[(warp * TN + h * 32 + lane) * 2 + 1] = t1;
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (tid < TN) {
+        run2 += ((rr[(0 * TN + tid) * 2] + rr[(1 * TN + tid) * 2]) + rr[(2 * TN + tid) * 2]) + rr[(3 * TN + tid) * 2];
+        run1 += ((rr[(0 * TN + tid) * 2 + 1] + rr[(1 * TN + tid) * 2 + 1]) + rr[(2 * TN + tid) * 2 + 1]) + rr[(3 * TN + tid) * 2 + 1];
+      }
+    }
+    if (tid < TN) {
+      const long long c = (long long)blockIdx.x * TN + tid;
+      const double vv = sf2 - run2;
+      var[c] = vv > 0.0 ? vv : (vv != vv ? vv : 0.0);
+      mean[c] = mconst + run1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+}
+
+bool g_attr_i8[16] = {false};
+
+}  // namespace
+
+int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count) {
+  slice_factor_kernel<<<dim3(Np / TM, count), 128, 0, ctx->stream>>>(fac, (long long)Np * Np, Np, facS, (long long)Np * Np * 8, sigma, s0);
+  b7_count(ctx);
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DT>
+static int launch_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N,
+                             int Np, const double* par, double inv_tau, int8_t* ksS) {
+  dim3 grid((unsigned)(rows_pad / TN), Np / KB);
+  if (kernel == B7_KERNEL_ARDSE) cov_slices_kernel<DT, B7_KERNEL_ARDSE><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
+  else cov_slices_kernel<DT, B7_KERNEL_MATERN52><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
+  b7_count(ctx);
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
+                     const double* par, double tau, int8_t* ksS) {
+  if (rows_pad <= 0) return 0;
+  const double inv_tau = 1.0 / tau;
+  if (d <= 8) return launch_cov_slices<8>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 16) return launch_cov_slices<16>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 24) return launch_cov_slices<24>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  return launch_cov_slices<40>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+}
+
+int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
+                           int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var) {
+  if (!g_attr_i8[ctx->device & 15]) {
+    B7_CUDA(cudaFuncSetAttribute(posterior_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    g_attr_i8[ctx->device & 15] = true;
+  }
+  if (cols_pad <= 0) return 0;
+  posterior_i8_kernel<<<(unsigned)(cols_pad / TN), I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, Np / TM, ksS, tau, sf2, mconst,
+                                                                                      mean, var);
+  b7_count(ctx);
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
