@@ -249,32 +249,41 @@ def main():
         gi = o_.value + row0 if o_.value > 0 else 0
         return parallel.allgather_argmax(b_.value, gi, n_.value) if world > 1 else (b_.value, gi, n_.value)
 
-    for _ in range(args.warmup):
-        res = step()
-    if dist:
-        dist.barrier()
-    ctx.sync()
-    ctx.reset_timers()
-    launches0 = ctx.launch_count()
-    with ClockSampler(local) as clk:
-        ctx.timer_begin()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = step()
-        dev_ms = ctx.timer_end()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-    if dist:
-        dist.barrier()
-    launches = ctx.launch_count() - launches0
-    st = ctx.stage_times()
-    ms = max(dev_ms, 0.0)
-    if dist:
-        import torch
-        t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, wall_ms = float(t[0]), float(t[1])
-    ms_per_step = ms / args.steps
+    def timed(path, warmup):
+        """K timed steps on the given posterior path; returns (device ms per step (max over ranks), wall ms, launches, stage times, clocks, result)."""
+        ctx.set_posterior_path(path)
+        for _ in range(warmup):
+            r = step()
+        if dist:
+            dist.barrier()
+        ctx.sync()
+        ctx.reset_timers()
+        l0 = ctx.launch_count()
+        with ClockSampler(local) as clk_:
+            ctx.timer_begin()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r = step()
+            dev = ctx.timer_end()
+            wall = (time.perf_counter() - t0) * 1e3
+        if dist:
+            dist.barrier()
+        n_l = ctx.launch_count() - l0
+        st_ = ctx.stage_times()
+        if dist:
+            import torch
+            t = torch.tensor([dev, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev, wall = float(t[0]), float(t[1])
+        return dev / args.steps, wall / args.steps, n_l, st_, clk_.summary(), r
+
+    default_path = ctx.posterior_path()
+    other_path = L.PATH_FP64_DMMA if default_path == L.PATH_INT8_OZAKI else L.PATH_INT8_OZAKI
+    # secondary path first (so that the default path is the one left selected), then the default path = `value`
+    o_ms, o_wall, o_launches, o_st, o_clk, o_res = timed(other_path, 2)
+    ms_per_step, wall_ms, launches, st, clocks, res = timed(default_path, args.warmup)
     value = world * M_STEP / (ms_per_step * 1e-3)
+    other_value = world * M_STEP / (o_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (fit + upload + score + read back) ------
     ctx.set_profiling(False)
@@ -323,18 +332,43 @@ def main():
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    post_ms, post_n = st["posterior"]
-    flops_per_launch = (SMS * 128) * (float(N_OBS) ** 2 + 4.0 * N_OBS)      # one panel x one draw (BASELINE.md section 4)
-    ach_tf = flops_per_launch / (post_ms / post_n * 1e-3) * 1e-12 if post_n else None
-    traffic = None
+    i8_peak, i8_src = 4010.5, "fallback constant"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "posterior_ncu_r01.json"))).get("dram_bytes_per_launch")
+        pk8 = json.load(open(os.path.join(ROOT, "profiles", "i8_mma_peak_r01.json")))
+        i8_peak = pk8["i8_mma_m128n128_tops"]
+        i8_src = "profiles/i8_mma_peak_r01.json: tcgen05.mma.kind::i8 M128 N128 issue-rate probe on this pool's B200 (tools/i8_mma_probe.cu)"
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "posterior_kernel (FP64 DMMA)", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (ach_tf / peak_tf) if ach_tf else None, "traffic": traffic, "peak_source": peak_src,
-                "launches_timed": post_n, "avg_launch_ms": post_ms / post_n if post_n else None,
-                "share_of_step": post_ms / ms if ms else None}
+    flops_per_launch = (SMS * 128) * (float(N_OBS) ** 2 + 4.0 * N_OBS)      # one panel x one draw (BASELINE.md section 4)
+
+    def posterior_roofline(path, st_, ms_step):
+        post_ms, post_n = st_["posterior"]
+        if not post_n:
+            return None
+        avg = post_ms / post_n
+        if path == L.PATH_FP64_DMMA:
+            ach = flops_per_launch / (avg * 1e-3) * 1e-12
+            return {"bound": "tensor", "kernel": "posterior_kernel (FP64 DMMA.8x8x4)", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src, "launches_timed": post_n, "avg_launch_ms": avg,
+                    "share_of_step": post_ms / (ms_step * args.steps)}
+        ach_eq = flops_per_launch / (avg * 1e-3) * 1e-12
+        ach_i8 = 36.0 * ach_eq                                                # 36 exact int8 slice products per fp64 product
+        return {"bound": "tensor", "kernel": "posterior_i8_kernel (tcgen05.mma.kind::i8, 8x8 error-free slices, 36 products)",
+                "achieved": ach_i8, "peak": i8_peak, "unit": "TOP/s", "frac": ach_i8 / i8_peak, "traffic": traffic_i8,
+                "fp64_equivalent_tflops": ach_eq, "fp64_dmma_peak_tflops": peak_tf, "peak_source": i8_src,
+                "note": "N = 64 MMAs (8 int32 accumulators x 64 columns fill the 512 TMEM columns) are shared-memory-bandwidth bound at "
+                        "2758 TOP/s in the same probe; the kernel runs at ~90 % of that",
+                "launches_timed": post_n, "avg_launch_ms": avg, "share_of_step": post_ms / (ms_step * args.steps)}
+
+    traffic = traffic_i8 = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "posterior_ncu_r01.json"))).get("dram_bytes_per_launch")
+        traffic_i8 = json.load(open(os.path.join(ROOT, "profiles", "posterior_i8_ncu_r01.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = posterior_roofline(default_path, st, ms_per_step)
+    roofline_other = posterior_roofline(other_path, o_st, o_ms)
+    path_name = {L.PATH_FP64_DMMA: "fp64_dmma", L.PATH_INT8_OZAKI: "int8_ozaki"}
     Np = N_OBS
     stages = {
         "kstar": {"ms_per_step": st["kstar"][0] / args.steps, "bound": "hbm",
@@ -353,6 +387,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "Hartmann6 integrated EI, N_obs=4096, d=6, S=32 draws (headline of BASELINE.json metric; fits one GPU)",
+                   "arithmetic": "fp64 results; on the int8_ozaki path the N^2 products are 36 exact int8 slice products recombined in fp64",
                    "kernel": "ARD-SE", "candidates_per_gpu_per_step": M_STEP, "grid": "Sobol (generated on device, per-rank shard)",
                    "l2": "inputs larger than L2: 32 inverse factors = 4.3 GB + 620 MB K* panel per launch vs 126 MB L2",
                    "parallelism": f"candidate-sharded x{world}" + (", draw-sharded fit + NCCL all-gather" if world > 1 else "")},
@@ -362,8 +397,12 @@ def main():
         "e2e": {"value": world * cnt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "includes": "b7_gp_fit from host X/y/hyp (K build, batched potrf, inversion) + b7_grid_from_host + b7_acq_score "
                             "with the score vector copied back", "seconds_per_step": e2e_s},
-        "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
-        "clocks": clk.summary(), "roofline": roofline, "stages": stages,
+        "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,
+        "clocks": clocks, "roofline": roofline, "stages": stages,
+        "posterior_path": path_name[default_path],
+        "other_path": {"posterior_path": path_name[other_path], "value": other_value, "unit": UNIT, "ms_per_step": o_ms,
+                       "gpu_launches": int(o_launches), "roofline": roofline_other, "clocks": o_clk,
+                       "same_argmax": bool(o_res[1] == res[1]), "best_rel_diff": abs(o_res[0] - res[0]) / abs(res[0]) if res[0] else None},
         "result": {"best": res[0], "global_index": res[1], "nan_count": res[2]},
     }
     if not args.no_cpu_baseline:

@@ -18,6 +18,7 @@ KERNEL_ARDSE, KERNEL_MATERN52 = 0, 1
 SCORE_EI, SCORE_CB = 0, 1
 BOUND_LOWER, BOUND_UPPER = 0, 1
 FIT_PREDICT, FIT_LOGML_ONLY, FIT_DEFER = 0, 1, 2
+PATH_FP64_DMMA, PATH_INT8_OZAKI = 0, 1
 STAGES = ("sobol", "kbuild", "potrf", "trtri", "kstar", "posterior", "score", "blr")
 
 _p = C.c_void_p
@@ -37,6 +38,8 @@ SIGNATURES = {
     "b7_set_profiling": (_i, [_p, _i]),
     "b7_reset_stage_timers": (_i, [_p]),
     "b7_last_stage_ms": (_i, [_p, _i, _dp, _lp]),
+    "b7_set_posterior_path": (_i, [_p, _i]),
+    "b7_get_posterior_path": (_i, [_p]),
     "b7_timer_begin": (_i, [_p]),
     "b7_timer_end": (_i, [_p, _dp]),
     "b7_launch_count": (_l, [_p]),
@@ -157,6 +160,12 @@ class Context:
             check(lib().b7_last_stage_ms(self.handle, k, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
         return out
+
+    def set_posterior_path(self, path: int):
+        check(lib().b7_set_posterior_path(self.handle, int(path)), "b7_set_posterior_path")
+
+    def posterior_path(self) -> int:
+        return int(lib().b7_get_posterior_path(self.handle))
 
     def timer_begin(self):
         check(lib().b7_timer_begin(self.handle), "b7_timer_begin")

@@ -180,7 +180,7 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
   B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = e && e[0] == '1'; }
+  { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));
@@ -215,6 +215,13 @@ int b7_sync(b7_ctx* ctx) {
   B7_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+
+int b7_set_posterior_path(b7_ctx* ctx, int path) {
+  if (!ctx || (path != B7_PATH_FP64_DMMA && path != B7_PATH_INT8_OZAKI)) { b7_set_error("set_posterior_path: bad arguments"); return B7_ERR_ARG; }
+  ctx->use_i8 = path == B7_PATH_INT8_OZAKI;
+  return 0;
+}
+int b7_get_posterior_path(b7_ctx* ctx) { return ctx && ctx->use_i8 ? B7_PATH_INT8_OZAKI : B7_PATH_FP64_DMMA; }
 
 int b7_timer_begin(b7_ctx* ctx) {
   if (!ctx) return B7_ERR_ARG;
@@ -489,7 +496,9 @@ static int gp_slice(b7_gp* gp, int s0, int count) {
     B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * fs * 8));
     B7_CHECK(dev_alloc(ctx, &gp->sigma, (size_t)gp->S * gp->Np));
   }
-  return b7_i8_slice_factor(ctx, gp->fac, gp->Np, gp->facS, gp->sigma, s0, count);
+  B7_CHECK(b7_i8_slice_factor(ctx, gp->fac, gp->Np, gp->facS, gp->sigma, s0, count));
+  for (int s = s0; s < s0 + count; ++s) gp->sliced[s] = 1;
+  return 0;
 }
 
 static int gp_invert(b7_gp* gp, int s0, int count) {
@@ -497,6 +506,7 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
   B7_CHECK(b7_launch_trtri(gp, s0, count));
+  for (int s = s0; s < s0 + count; ++s) gp->sliced[s] = 0;
   if (ctx->use_i8) B7_CHECK(gp_slice(gp, s0, count));
   t.stop((int)(ctx->launches - before));
   return 0;
@@ -505,6 +515,7 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
 int b7_gp_mark_ready(b7_gp* gp) {
   if (!gp) return B7_ERR_ARG;
   // slots filled by the host (all-gather into fac, which already is the layout the posterior pass reads)
+  std::fill(gp->sliced.begin(), gp->sliced.end(), 0);
   if (gp->ctx->use_i8) {
     B7_CUDA(cudaSetDevice(gp->ctx->device));
     B7_CHECK(gp_slice(gp, 0, gp->S));
@@ -528,7 +539,7 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
   b7_gp* gp = new b7_gp();
   gp->ctx = ctx; gp->kernel = kernel; gp->N = N; gp->d = d; gp->S = S; gp->noiseless = noiseless;
   gp->Np = (int)pad128(N); gp->NB = gp->Np / B7_NB;
-  gp->jitter.assign(S, 0.0); gp->info_host.assign(S, 0); gp->logml_host.assign(S, 0.0);
+  gp->jitter.assign(S, 0.0); gp->info_host.assign(S, 0); gp->logml_host.assign(S, 0.0); gp->sliced.assign(S, 0);
   const size_t Np = gp->Np, fs = Np * Np, ds = (size_t)gp->NB * B7_NB * B7_NB;
   int rc = 0;
   auto fail = [&](int code) { b7_gp_free(gp); return code; };
@@ -631,6 +642,7 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
   const double* p = gp->par_host.data() + (size_t)s * kParStride;
   if (ctx->use_i8) {
+    if (!gp->sliced[s]) B7_CHECK(gp_slice(gp, s, 1));     // the path was switched after the fit
     // error-free sliced operands on the INT8 tensor pipe (posterior_i8.cu); K* needs no max: 0 < k* <= sf2 <= tau
     int e = 0;
     frexp(p[B7_MAX_DIMS], &e);

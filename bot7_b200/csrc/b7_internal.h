@@ -81,6 +81,7 @@ struct b7_gp {
   double* tt = nullptr;     // device S x (128 x Np tiled) : scratch of the inversion sweep
   double* logdet = nullptr; // device S : sum log L_ii
   int* info = nullptr;      // device S
+  std::vector<char> sliced;   // per draw: facS/sigma hold the slices of the current L^-1
   std::vector<double> jitter;
   std::vector<int> info_host;
   std::vector<double> logml_host;

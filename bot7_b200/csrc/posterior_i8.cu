@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include "b7_internal.h"
+#include "exp_neg.cuh"
 #include "gemm_tile.cuh"
 
 using b7g::mbar_init; using b7g::mbar_wait; using b7g::mbar_arrive; using b7g::mbar_arrive_expect_tx; using b7g::bulk_g2s;
@@ -59,14 +60,17 @@ slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np
   const double* src = fac + (long long)s * fac_stride + b7g::tile_off(KTA, rb, 0);
   const int k_end = (rb + 1) * TM;
   double mx = 0.0;
+  bool bad = false;
   for (int k4 = 0; k4 < k_end; k4 += 4) {
     const double* p = src + b7g::elem_off(row, k4);
+    bad |= !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]));
     mx = fmax(mx, fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3]))));
   }
   int e = 0;
   frexp(mx, &e);                                   // mx = f 2^e, f in [0.5, 1)  ->  2^e > mx
-  const double sg = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, e) : 1.0;
-  const double inv = 1.0 / sg;
+  // a failed factorisation (NaN / inf in the row) must poison the results like it does on the fp64 path
+  const double sg = bad ? __longlong_as_double(0x7ff8000000000000LL) : (mx > 0.0 ? ldexp(1.0, e) : 1.0);
+  const double inv = bad ? 0.0 : 1.0 / sg;
   sigma[(long long)s * Np + rb * TM + row] = sg;
   int8_t* dst = facS + (long long)s * facS_stride + (long long)rb * KS_ALL * A_STAGE;
   for (int kc = 0; kc < k_end / 16; ++kc) {
@@ -95,6 +99,8 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
                   const double* __restrict__ par, double inv_tau, int8_t* __restrict__ ksS) {
   __shared__ double s_x[DT][KB];
   __shared__ double s_w[DT];
+  __shared__ double s_tab[64];
+  if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
   const int ct = blockIdx.x, ks = blockIdx.y, KS_ALL = Np / KB;
   const int c = threadIdx.x & 63, kc = threadIdx.x >> 6;          // warp = 32 consecutive candidates, one k chunk
   for (int e = threadIdx.x; e < DT * KB; e += 256) {
@@ -123,10 +129,10 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
         r2 = fma(t, t, r2);
       }
       if (KERNEL == B7_KERNEL_ARDSE) {
-        val = sf2 * exp(-0.5 * r2);
+        val = sf2 * exp_neg(-0.5 * r2, s_tab);
       } else {
         const double rr = sqrt(r2), s5r = 2.23606797749978969641 * rr;
-        val = sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp(-s5r));
+        val = sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp_neg(-s5r, s_tab));
       }
     }
     int dg[NS];
@@ -248,7 +254,8 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
           mbar_wait(full + slot, (unsigned)((it / NSTAGE) & 1));
           tc_fence_after();
           const uint8_t* sa = smem + slot * STAGE;
-          const uint8_t* sb = sa + A_STAGE;
+          // descriptors of slice 1 / first k half; the others differ only in the 16-byte-unit address field
+          const uint64_t da0 = umma_desc(sa, TM * 16, 128), db0 = umma_desc(sa + A_STAGE, TN * 16, 128);
 #pragma unroll
           for (int k2 = 0; k2 < KB / 32; ++k2) {
 #pragma unroll
@@ -257,8 +264,8 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
               for (int p = 1; p <= NS; ++p) {
                 const int q = w - p;
                 if (q < 1 || q > NS) continue;
-                const uint64_t da = umma_desc(sa + (p - 1) * (4 * TM * 16) + k2 * (2 * TM * 16), TM * 16, 128);
-                const uint64_t db = umma_desc(sb + (q - 1) * (4 * TN * 16) + k2 * (2 * TN * 16), TN * 16, 128);
+                const uint64_t da = da0 + (uint64_t)(((p - 1) * (4 * TM * 16) + k2 * (2 * TM * 16)) >> 4);
+                const uint64_t db = db0 + (uint64_t)(((q - 1) * (4 * TN * 16) + k2 * (2 * TN * 16)) >> 4);
                 const bool first = (ks == 0 && k2 == 0 && p == (w - NS > 1 ? w - NS : 1));
                 umma_i8(tmem + (uint32_t)((w - 2) * TN), da, db, idesc, first ? 0u : 1u);
               }
@@ -351,6 +358,9 @@ int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int
                      const double* par, double tau, int8_t* ksS) {
   if (rows_pad <= 0) return 0;
   const double inv_tau = 1.0 / tau;
+  if (d <= 2) return launch_cov_slices<2>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 4) return launch_cov_slices<4>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 6) return launch_cov_slices<6>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
   if (d <= 8) return launch_cov_slices<8>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
   if (d <= 16) return launch_cov_slices<16>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
   if (d <= 24) return launch_cov_slices<24>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);

@@ -46,6 +46,14 @@ int  b7_sync(b7_ctx* ctx);
 int  b7_set_profiling(b7_ctx* ctx, int on);   /* off by default: stage timing synchronises per launch */
 int  b7_reset_stage_timers(b7_ctx* ctx);
 int  b7_last_stage_ms(b7_ctx* ctx, int stage, double* ms_total, int64_t* launches);
+/* Which tensor pipe carries the posterior pass (V = L^-1 K*^T, N^2 flop per candidate per draw):
+ *   B7_PATH_FP64_DMMA  fp64 operands on DMMA tiles (posterior.cu);
+ *   B7_PATH_INT8_OZAKI both operands split error-free into 8 int8 slices, 36 exact int32 products on
+ *                      tcgen05.mma.kind::i8, recombined in fp64 (posterior_i8.cu): same results to ~1e-14 sf2,
+ *                      about twice the throughput.  Default; B7_POSTERIOR_I8=0 in the environment selects DMMA. */
+enum { B7_PATH_FP64_DMMA = 0, B7_PATH_INT8_OZAKI = 1 };
+int  b7_set_posterior_path(b7_ctx* ctx, int path);
+int  b7_get_posterior_path(b7_ctx* ctx);
 /* device-side stopwatch: CUDA events recorded on the context stream (begin; ...calls...; end -> ms) */
 int  b7_timer_begin(b7_ctx* ctx);
 int  b7_timer_end(b7_ctx* ctx, double* ms);

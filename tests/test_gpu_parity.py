@@ -262,6 +262,38 @@ def test_jitter_retry_policy_matches_reference_policy(ctx, oracle, capsys):
     f.free()
 
 
+def test_both_posterior_paths_agree_with_the_oracle(ctx, oracle):
+    # FP64 DMMA tiles vs error-free int8 slices on tcgen05 (36 exact products recombined in fp64): same handle,
+    # path switched on the fly; both against the oracle and against each other
+    Xo, y, hyp, Xc = make_problem(oracle, 900, 6, 3, 12000, 1e-2)
+    f = models.GPFactors(Xo, y, hyp)
+    grid = grids.DeviceGrid.from_host(Xc)
+    ref = oracle.acquisition(Xo, y, hyp, Xc, 0, False, oracle.SCORE_EI)
+    keep = ctx.posterior_path()
+    out = {}
+    try:
+        for path in (L.PATH_FP64_DMMA, L.PATH_INT8_OZAKI, L.PATH_FP64_DMMA):
+            ctx.set_posterior_path(path)
+            assert ctx.posterior_path() == path
+            mv = [f.predict(s, Xc) for s in range(3)]
+            sc = np.empty(Xc.shape[0])
+            am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+            L.check(L.lib().b7_acq_score(f.handle, grid.handle, L.SCORE_EI, 0.0, 0, -1.0, float(y.min()), L.dptr(sc), C.byref(am),
+                                         C.byref(amo), C.byref(best), C.byref(nn)))
+            for s in range(3):
+                sf2 = np.exp(2 * hyp[s, 6])
+                assert rel(mv[s][0], ref["mean"][s], 1.0) <= 1e-9 and rel(mv[s][1], ref["var"][s], sf2) <= 1e-9
+            assert am.value == ref["idx"] and rel(sc, ref["score"], 1e-6 * ref["score"].max()) <= 1e-7
+            out[path] = (mv, sc)
+    finally:
+        ctx.set_posterior_path(keep)
+    a, b = out[L.PATH_FP64_DMMA], out[L.PATH_INT8_OZAKI]
+    for s in range(3):
+        assert np.max(np.abs(a[0][s][1] - b[0][s][1])) <= 1e-12 * np.exp(2 * hyp[s, 6])      # variance: 1e-12 sf2
+        assert np.max(np.abs(a[0][s][0] - b[0][s][0])) <= 1e-10
+    f.free()
+
+
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
     Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 3, 2000, 1e-2)
     a = models.GPFactors(Xo, y, hyp)

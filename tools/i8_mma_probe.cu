@@ -49,7 +49,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(s32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int M = 128, N = 128, K = 64;   // K in int8 elements (2 instructions of K = 32)
+#ifndef PN
+#define PN 128
+#endif
+constexpr int M = 128, N = PN, K = 64;   // K in int8 elements (2 instructions of K = 32)
 
 template <bool PERF>
 __global__ void __launch_bounds__(128, 1) probe(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int* __restrict__ D, int iters) {
