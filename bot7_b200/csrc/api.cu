@@ -488,12 +488,15 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
   }
 }
 
+// the INT8 path keeps exact int32 sums only up to B7_I8_MAX_NP observations; larger fits stay on the FP64 DMMA kernel
+static bool i8_path(const b7_gp* gp) { return gp->ctx->use_i8 && gp->Np <= B7_I8_MAX_NP; }
+
 // INT8 path: slice L^-1 (allocated on first use)
 static int gp_slice(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
   const size_t fs = (size_t)gp->Np * gp->Np;
   if (!gp->facS) {
-    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * fs * 8));
+    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * fs * B7_I8_SLICES));
     B7_CHECK(dev_alloc(ctx, &gp->sigma, (size_t)gp->S * gp->Np));
   }
   B7_CHECK(b7_i8_slice_factor(ctx, gp->fac, gp->Np, gp->facS, gp->sigma, s0, count));
@@ -507,7 +510,7 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
   int64_t before = ctx->launches;
   B7_CHECK(b7_launch_trtri(gp, s0, count));
   for (int s = s0; s < s0 + count; ++s) gp->sliced[s] = 0;
-  if (ctx->use_i8) B7_CHECK(gp_slice(gp, s0, count));
+  if (i8_path(gp)) B7_CHECK(gp_slice(gp, s0, count));
   t.stop((int)(ctx->launches - before));
   return 0;
 }
@@ -516,7 +519,7 @@ int b7_gp_mark_ready(b7_gp* gp) {
   if (!gp) return B7_ERR_ARG;
   // slots filled by the host (all-gather into fac, which already is the layout the posterior pass reads)
   std::fill(gp->sliced.begin(), gp->sliced.end(), 0);
-  if (gp->ctx->use_i8) {
+  if (i8_path(gp)) {
     B7_CUDA(cudaSetDevice(gp->ctx->device));
     B7_CHECK(gp_slice(gp, 0, gp->S));
     B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
@@ -641,7 +644,7 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   const int64_t rp = pad128(rows);
   B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
   const double* p = gp->par_host.data() + (size_t)s * kParStride;
-  if (ctx->use_i8) {
+  if (i8_path(gp)) {
     if (!gp->sliced[s]) B7_CHECK(gp_slice(gp, s, 1));     // the path was switched after the fit
     // error-free sliced operands on the INT8 tensor pipe (posterior_i8.cu); K* needs no max: 0 < k* <= sf2 <= tau
     int e = 0;
@@ -655,7 +658,7 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
       t.stop(1);
     }
     StageTimer t(ctx, ST_POSTERIOR);
-    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * 8, gp->sigma + (size_t)s * gp->Np,
+    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * B7_I8_SLICES, gp->sigma + (size_t)s * gp->Np,
                                     gp->beta + (size_t)s * gp->Np, gp->Np, ksS, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
     t.stop(1);
     return 0;

@@ -73,7 +73,7 @@ struct b7_gp {
   std::vector<double> par_host;
   std::vector<double> y_host;   // observations kept on the host for the residual upload of refits / retries
   double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1, lower, in the tiled (fragment-order) layout
-  int8_t* facS = nullptr;   // device S x Np x Np x 8 : 8 int8 slices of L^-1 (only with ctx->use_i8)
+  int8_t* facS = nullptr;   // device S x Np x Np x B7_I8_SLICES : int8 slices of L^-1 (only with ctx->use_i8)
   double* sigma = nullptr;  // device S x Np : per-row power-of-two scales of the slices
   double* dinv = nullptr;   // device S x NB x (128 x 128 tiled) : inverse of the diagonal blocks of L
   double* dinvT = nullptr;  // device, transposes of dinv (tiled)
@@ -134,6 +134,8 @@ int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out /* N x N row-m
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
 // posterior_i8.cu
+#define B7_I8_SLICES 7        // radix-256 digit slices per operand
+#define B7_I8_MAX_NP 16384    // 7 products x 2^14 x Np must stay below 2^31
 int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count);
 int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
                      const double* par, double tau, int8_t* ksS);

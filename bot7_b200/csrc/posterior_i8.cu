@@ -4,18 +4,21 @@
 // same fp64-level accuracy, but the N^2 product per candidate runs on tcgen05.mma.kind::i8 (measured
 // 3.9 POPS on B200, tools/i8_mma_probe.cu, against 37 TFLOP/s for the FP64 DMMA pipe) through an
 // error-free slicing of both operands (the "Ozaki scheme"):
-//     a_ik = sigma_i * sum_{p=1..8} d_p(i,k) 2^-(7p-1),   d_p integers in [-64, 64]   (55 bits per entry)
-//     b_ck = tau     * sum_{q=1..8} e_q(c,k) 2^-(7q-1)
-//     v_ic = sigma_i tau sum_{w=2..9} 2^(2-7w) sum_{p+q=w} sum_k d_p(i,k) e_q(c,k)
-// Every inner sum is an exact int32 dot product (|d e| <= 2^12, k <= 2^17 terms would still fit), the 36
-// slice pairs with p + q <= 9 are kept (the dropped ones are below 2^-56 of sigma_i tau N), and the 8 weight
-// classes are accumulated in 8 x 64 = 512 TMEM columns and combined in fp64 in the epilogue.  Measured
-// against the fp64 path: variance within 1e-14 sf2, mean within 1e-12 (see tests).
+//     a_ik = sigma_i * sum_{p=1..7} d_p(i,k) 2^-(8p-2),   d_p integers in [-128, 127]  (54 bits + sign per entry)
+//     b_ck = tau     * sum_{q=1..7} e_q(c,k) 2^-(8q-2)
+//     v_ic = sigma_i tau sum_{w=2..8} 2^(4-8w) sum_{p+q=w} sum_k d_p(i,k) e_q(c,k)
+// Every inner sum is an exact int32 dot product (|d e| <= 2^14, a class holds at most 7 products, so
+// k <= 16384 terms fit), the 28 slice pairs with p + q <= 8 are kept (the dropped ones are below 2^-54 of
+// sigma_i tau per term), and the 7 weight classes are accumulated in 7 x 64 = 448 TMEM columns and combined
+// in fp64 in the epilogue.  Measured against the fp64 path: variance within 1e-13 sf2, mean within 1e-12
+// (see tests).
 //
 // One CTA owns 64 candidates and walks the row blocks of L^-1 (128 rows = TMEM lanes).  Warp roles:
-// warp 4 lane 0 streams the slices (already in the UMMA canonical K-major layout in HBM, so a stage is six
-// 16 KB bulk copies), warp 5 lane 0 issues the 72 MMAs of a stage, warps 0-3 drain the accumulators once
-// per row block (tcgen05.ld), rebuild v in fp64 and reduce v^2 and v*beta over the 128 rows.
+// warp 4 lane 0 streams the slices (already in the UMMA canonical K-major layout in HBM, so a stage is two
+// bulk copies), warp 5 lane 0 issues the MMAs of a stage, warps 0-3 drain the accumulators once per row
+// block (tcgen05.ld), rebuild v in fp64 and reduce v^2 and v*beta over the 128 rows.  The MMAs are issued
+// slice-of-L^-1-major so that the 4 KB A operand stays in the tensor core's collector while it meets its
+// 8 - p partner slices of K* (tcgen05.mma ... collector::a::fill / use / lastuse).
 #include <math.h>
 
 #include "b7_internal.h"
@@ -27,31 +30,43 @@ using b7g::mbar_fence_init; using b7g::smem_u32;
 
 namespace {
 
-constexpr int NS = 8;                      // slices per operand
-constexpr int TM = 128, TN = 64, KB = 64;  // L^-1 rows per block, candidates per CTA, k bytes per stage
-constexpr int A_STAGE = NS * TM * KB;      // 65536 B
-constexpr int B_STAGE = NS * TN * KB;      // 32768 B
-constexpr int STAGE = A_STAGE + B_STAGE;   // 98304 B
-constexpr int NSTAGE = 2;
+#ifndef I8_KB
+#define I8_KB 64
+#endif
+#ifndef I8_NSTAGE
+#define I8_NSTAGE 2
+#endif
+constexpr int NS = B7_I8_SLICES;           // slices per operand (7)
+constexpr int TM = 128, TN = 64, KB = I8_KB;  // L^-1 rows per block, candidates per CTA, k bytes per stage
+constexpr int KC = KB / 16;                // 16-byte k chunks per stage
+constexpr int A_STAGE = NS * TM * KB;      // 57344 B
+constexpr int B_STAGE = NS * TN * KB;      // 28672 B
+constexpr int STAGE = A_STAGE + B_STAGE;   // 86016 B
+constexpr int NSTAGE = I8_NSTAGE;
+static_assert(STAGE % 1024 == 0 && KB % 32 == 0 && 64 % KB == 0, "stage geometry");
 constexpr int I8_THREADS = 192;
 constexpr int RED_BYTES = 2 * 4 * TN * 2 * 8;           // [rb parity][warp][candidate][sum v^2, sum v beta]
 constexpr int I8_SMEM = NSTAGE * STAGE + RED_BYTES + 1024;   // stages + reduction scratch + barriers
 
 // ---- slicing -------------------------------------------------------------------------------------------
 
-// 8 signed 7-bit digits of t in [-1, 1]:  t = sum_p d_p 2^-(7p-1) + O(2^-56); every step is exact in fp64
-__device__ __forceinline__ void digits8(double t, int (&d)[NS]) {
+// 7 signed digits of t in (-1, 1):  t = sum_p d_p 2^-(8p-2) + O(2^-54), d_1 in [-64, 64], the others radix 256
+// in [-128, 127].  A radix-256 digit set without redundancy only closes if every remainder stays inside
+// [-128/255, 127/255), hence the floor(r + 128/255) rounding; the clamp catches the ulp-wide boundary cases
+// (the excess moves to the next digit and ends below the truncation level).
+__device__ __forceinline__ void digits7(double t, int (&d)[NS]) {
   double r = t * 64.0;
 #pragma unroll
   for (int p = 0; p < NS; ++p) {
-    const double q = rint(r);
+    double q = floor(r + (128.0 / 255.0));
+    if (p > 0) q = fmin(fmax(q, -128.0), 127.0);
     d[p] = (int)q;
-    r = (r - q) * 128.0;
+    r = (r - q) * 256.0;
   }
 }
 
 // L^-1 (tiled fp64, lower) -> per-row power-of-two scale sigma and the slice array
-// facS[rb][ks][p][kc][row][16]  (ks = 64-column stage, kc = 16-column chunk inside it)
+// facS[rb][ks][p][kc][row][16]  (ks = KB-column stage, kc = 16-column chunk inside it)
 __global__ void __launch_bounds__(128)
 slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np, int8_t* __restrict__ facS,
                     long long facS_stride, double* __restrict__ sigma, int s0) {
@@ -80,32 +95,32 @@ slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       int d[NS];
-      digits8(src[b7g::elem_off(row, kc * 16 + i)] * inv, d);
+      digits7(src[b7g::elem_off(row, kc * 16 + i)] * inv, d);
 #pragma unroll
       for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(d[p] & 0xff)) << (8 * (i & 3));
     }
-    const int ks = kc >> 2, kcc = kc & 3;
+    const int ks = kc / KC, kcc = kc % KC;
 #pragma unroll
     for (int p = 0; p < NS; ++p)
-      *reinterpret_cast<uint4*>(dst + (long long)ks * A_STAGE + p * (4 * TM * 16) + kcc * (TM * 16) + row * 16) =
+      *reinterpret_cast<uint4*>(dst + (long long)ks * A_STAGE + p * (KC * TM * 16) + kcc * (TM * 16) + row * 16) =
           make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
   }
 }
 
-// K(X*, X) evaluated and sliced in one pass: ksS[ct][ks][q][kc][cand 64][16]; one block per (candidate tile, stage)
+// K(X*, X) evaluated and sliced in one pass: ksS[ct][ks][q][kc][cand 64][16]; one block per (candidate tile, 64 columns)
 template <int DT, int KERNEL>
 __global__ void __launch_bounds__(256)
 cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const double* __restrict__ Xt, int N, int Np,
                   const double* __restrict__ par, double inv_tau, int8_t* __restrict__ ksS) {
-  __shared__ double s_x[DT][KB];
+  __shared__ double s_x[DT][64];
   __shared__ double s_w[DT];
   __shared__ double s_tab[64];
   if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
-  const int ct = blockIdx.x, ks = blockIdx.y, KS_ALL = Np / KB;
+  const int ct = blockIdx.x, kb64 = blockIdx.y, KS_ALL = Np / KB;
   const int c = threadIdx.x & 63, kc = threadIdx.x >> 6;          // warp = 32 consecutive candidates, one k chunk
-  for (int e = threadIdx.x; e < DT * KB; e += 256) {
-    const int i = e / KB, k = ks * KB + e % KB;
-    s_x[i][e % KB] = (i < d && k < N) ? Xt[(long long)i * Np + k] : 0.0;
+  for (int e = threadIdx.x; e < DT * 64; e += 256) {
+    const int i = e / 64, k = kb64 * 64 + e % 64;
+    s_x[i][e % 64] = (i < d && k < N) ? Xt[(long long)i * Np + k] : 0.0;
   }
   if (threadIdx.x < DT) s_w[threadIdx.x] = threadIdx.x < d ? par[threadIdx.x] : 0.0;
   __syncthreads();
@@ -119,7 +134,7 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
   for (int p = 0; p < NS; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int kk = kc * 16 + i, k = ks * KB + kk;
+    const int kk = kc * 16 + i, k = kb64 * 64 + kk;
     double val = 0.0;
     if (row < rows && k < N) {
       double r2 = 0.0;
@@ -136,13 +151,14 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
       }
     }
     int dg[NS];
-    digits8(val * inv_tau, dg);
+    digits7(val * inv_tau, dg);
 #pragma unroll
     for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(dg[p] & 0xff)) << (8 * (i & 3));
   }
-  int8_t* dst = ksS + ((long long)ct * KS_ALL + ks) * B_STAGE + kc * (TN * 16) + c * 16;
+  const int gkc = kb64 * 4 + kc, ks = gkc / KC, kcc = gkc % KC;
+  int8_t* dst = ksS + ((long long)ct * KS_ALL + ks) * B_STAGE + kcc * (TN * 16) + c * 16;
 #pragma unroll
-  for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (4 * TN * 16)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (KC * TN * 16)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
 }
 
 // ---- tcgen05 helpers -----------------------------------------------------------------------------------
@@ -155,11 +171,24 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem, int lbo_bytes, i
   d |= (uint64_t)1 << 46;                             // sm_100 descriptor version; SWIZZLE_NONE
   return d;
 }
+// HINT: 0 = plain, 1 = keep A in the collector (fill), 2 = A from the collector and keep it (use),
+// 3 = A from the collector, then release it (lastuse).  SASS: UTCIMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE
+template <int HINT>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
+#define B7_UMMA_I8(QUAL)                                                                                            \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t}\n" \
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory")
+  if (HINT == 1) B7_UMMA_I8(".collector::a::fill");
+  else if (HINT == 2) B7_UMMA_I8(".collector::a::use");
+  else if (HINT == 3) B7_UMMA_I8(".collector::a::lastuse");
+  else B7_UMMA_I8("");
+#undef B7_UMMA_I8
+}
+// one lane of a converged warp (all 32 lanes must call it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -223,57 +252,66 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    // ---- producer: stream (rb, ks) stages ----
-    if (lane == 0) {
-      const int8_t* gB = ksS + (long long)blockIdx.x * KS_ALL * B_STAGE;
-      long long it = 0;
-      for (int rb = 0; rb < NB; ++rb)
-        for (int ks = 0; ks < 2 * (rb + 1); ++ks, ++it) {
-          const int slot = (int)(it % NSTAGE);
-          if (it >= NSTAGE) mbar_wait(empty + slot, (unsigned)(((it / NSTAGE) - 1) & 1));
+    // ---- producer: stream (rb, ks) stages.  The whole warp walks the loop and one elected lane issues the
+    // copies: under `if (lane == 0)` the compiler wraps every uniform-datapath instruction (UBLKCP, UTCIMMA) in
+    // an ELECT / BRA.U.ANY serialisation loop, which made the MMA issue the bottleneck (61 clk per MMA). ----
+    const int8_t* gB = ksS + (long long)blockIdx.x * KS_ALL * B_STAGE;
+    int slot = 0;
+    unsigned phase = 1;                    // parity of the *previous* use of the slot; first round needs no wait
+    bool wrapped = false;
+    for (int rb = 0; rb < NB; ++rb)
+      for (int ks = 0; ks < (TM / KB) * (rb + 1); ++ks) {
+        if (wrapped) mbar_wait(empty + slot, phase);
+        if (elect_one()) {
           uint8_t* st = smem + slot * STAGE;
           mbar_arrive_expect_tx(full + slot, STAGE);
-          const int8_t* a = facS + ((long long)rb * KS_ALL + ks) * A_STAGE;
-          const int8_t* b = gB + (long long)ks * B_STAGE;
-#pragma unroll
-          for (int c = 0; c < A_STAGE / 16384; ++c) bulk_g2s(st + c * 16384, a + c * 16384, 16384, full + slot);
-#pragma unroll
-          for (int c = 0; c < B_STAGE / 16384; ++c) bulk_g2s(st + A_STAGE + c * 16384, b + c * 16384, 16384, full + slot);
+          bulk_g2s(st, facS + ((long long)rb * KS_ALL + ks) * A_STAGE, A_STAGE, full + slot);
+          bulk_g2s(st + A_STAGE, gB + (long long)ks * B_STAGE, B_STAGE, full + slot);
         }
-    }
+        __syncwarp();
+        if (++slot == NSTAGE) { slot = 0; phase ^= 1u; wrapped = true; }
+      }
   } else if (warp == 5) {
-    // ---- MMA issuer ----
-    if (lane == 0) {
-      // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      long long it = 0;
-      for (int rb = 0; rb < NB; ++rb) {
-        if (rb > 0) { mbar_wait(acc_empty, (unsigned)((rb - 1) & 1)); tc_fence_after(); }
-        for (int ks = 0; ks < 2 * (rb + 1); ++ks, ++it) {
-          const int slot = (int)(it % NSTAGE);
-          mbar_wait(full + slot, (unsigned)((it / NSTAGE) & 1));
-          tc_fence_after();
+    // ---- MMA issuer (warp-converged, one elected lane) ----
+    // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    int slot = 0;
+    unsigned phase = 0;
+    for (int rb = 0; rb < NB; ++rb) {
+      if (rb > 0) { mbar_wait(acc_empty, (unsigned)((rb - 1) & 1)); tc_fence_after(); }
+      const int n_ks = (TM / KB) * (rb + 1);
+      for (int ks = 0; ks < n_ks; ++ks) {
+        mbar_wait(full + slot, phase);
+        tc_fence_after();
+        if (elect_one()) {
           const uint8_t* sa = smem + slot * STAGE;
           // descriptors of slice 1 / first k half; the others differ only in the 16-byte-unit address field
           const uint64_t da0 = umma_desc(sa, TM * 16, 128), db0 = umma_desc(sa + A_STAGE, TN * 16, 128);
 #pragma unroll
           for (int k2 = 0; k2 < KB / 32; ++k2) {
+            // slice p of L^-1 meets slices 1 .. NS + 1 - p of K*; class p + q accumulates in its own 64 columns,
+            // and every class sees its first product in the p = 1 group
 #pragma unroll
-            for (int w = 2; w <= NS + 1; ++w) {
+            for (int p = 1; p <= NS; ++p) {
+              const uint64_t da = da0 + (uint64_t)(((p - 1) * (KC * TM * 16) + k2 * (2 * TM * 16)) >> 4);
+              const uint32_t acc = (ks == 0 && k2 == 0 && p == 1) ? 0u : 1u;
+              const int nq = NS + 1 - p;
 #pragma unroll
-              for (int p = 1; p <= NS; ++p) {
-                const int q = w - p;
-                if (q < 1 || q > NS) continue;
-                const uint64_t da = da0 + (uint64_t)(((p - 1) * (4 * TM * 16) + k2 * (2 * TM * 16)) >> 4);
-                const uint64_t db = db0 + (uint64_t)(((q - 1) * (4 * TN * 16) + k2 * (2 * TN * 16)) >> 4);
-                const bool first = (ks == 0 && k2 == 0 && p == (w - NS > 1 ? w - NS : 1));
-                umma_i8(tmem + (uint32_t)((w - 2) * TN), da, db, idesc, first ? 0u : 1u);
+              for (int q = 1; q <= nq; ++q) {
+                const uint64_t db = db0 + (uint64_t)(((q - 1) * (KC * TN * 16) + k2 * (2 * TN * 16)) >> 4);
+                const uint32_t dcol = tmem + (uint32_t)((p + q - 2) * TN);
+                if (nq == 1) umma_i8<0>(dcol, da, db, idesc, acc);
+                else if (q == 1) umma_i8<1>(dcol, da, db, idesc, acc);
+                else if (q == nq) umma_i8<3>(dcol, da, db, idesc, acc);
+                else umma_i8<2>(dcol, da, db, idesc, acc);
               }
             }
           }
-          umma_commit(empty + slot);       // frees the stage once these MMAs have read it
+          umma_commit(empty + slot);                   // frees the stage once these MMAs have read it
+          if (ks == n_ks - 1) umma_commit(acc_full);   // all MMAs of the row block done -> epilogue may read TMEM
         }
-        umma_commit(acc_full);             // all MMAs of the row block done -> epilogue may read TMEM
+        __syncwarp();
+        if (++slot == NSTAGE) { slot = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -287,7 +325,7 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
       for (int c = 0; c < TN; ++c) v[c] = 0.0;
 #pragma unroll
       for (int w = 2; w <= NS + 1; ++w) {
-        const double wt = ldexp(1.0, 2 - 7 * w);
+        const double wt = ldexp(1.0, 4 - 8 * w);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t dv[32];
@@ -337,7 +375,7 @@ bool g_attr_i8[16] = {false};
 }  // namespace
 
 int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count) {
-  slice_factor_kernel<<<dim3(Np / TM, count), 128, 0, ctx->stream>>>(fac, (long long)Np * Np, Np, facS, (long long)Np * Np * 8, sigma, s0);
+  slice_factor_kernel<<<dim3(Np / TM, count), 128, 0, ctx->stream>>>(fac, (long long)Np * Np, Np, facS, (long long)Np * Np * NS, sigma, s0);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;
@@ -346,7 +384,7 @@ int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, dou
 template <int DT>
 static int launch_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N,
                              int Np, const double* par, double inv_tau, int8_t* ksS) {
-  dim3 grid((unsigned)(rows_pad / TN), Np / KB);
+  dim3 grid((unsigned)(rows_pad / TN), Np / 64);
   if (kernel == B7_KERNEL_ARDSE) cov_slices_kernel<DT, B7_KERNEL_ARDSE><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
   else cov_slices_kernel<DT, B7_KERNEL_MATERN52><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
   b7_count(ctx);

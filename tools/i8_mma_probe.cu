@@ -41,6 +41,18 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same MMA with an A-collector hint: 1 = fill (keep A for the next instruction), 2 = use (A comes from the collector, keep it),
+// 3 = lastuse (A comes from the collector, then released).  SASS: UTCIMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE
+template <int HINT>
+__device__ __forceinline__ void mma_i8_coll(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (HINT == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  else if (HINT == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  else if (HINT == 3)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  else mma_i8(tmem_d, da, db, idesc, accumulate);
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(s32(bar)) : "memory");
 }
@@ -54,7 +66,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 #endif
 constexpr int M = 128, N = PN, K = 64;   // K in int8 elements (2 instructions of K = 32)
 
-template <bool PERF>
+// one lane of a converged warp; unlike `if (lane == 0)` this lets the compiler issue UTCIMMA directly instead of wrapping
+// every instruction in an ELECT / BRA.U.ANY serialisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
+#ifndef PG
+#define PG 4          // MMAs per A tile in the collector experiment (the posterior kernel averages 4.5)
+#endif
+template <bool PERF, bool COLL>
 __global__ void __launch_bounds__(128, 1) probe(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int* __restrict__ D, int iters) {
   __shared__ __align__(1024) int8_t sA[M * K];
   __shared__ __align__(1024) int8_t sB[N * K];
@@ -74,13 +96,27 @@ __global__ void __launch_bounds__(128, 1) probe(const int8_t* __restrict__ A, co
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base;
   const uint32_t idesc = make_idesc_i8(M, N);
+#ifdef PROBE_LANE0
   if (tid == 0) {
+#else
+  if (warp == 0 && elect_one()) {
+#endif
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int kk = 0; kk < K / 32; ++kk) {
         const uint64_t da = make_desc(sA + kk * 2 * (M * 16), M * 16, 128);
         const uint64_t db = make_desc(sB + kk * 2 * (N * 16), N * 16, 128);
-        mma_i8(tmem, da, db, idesc, (PERF ? 1u : (uint32_t)(it > 0 || kk > 0)));
+        if (!COLL) { mma_i8(tmem, da, db, idesc, (PERF ? 1u : (uint32_t)(it > 0 || kk > 0))); continue; }
+        // collector experiment: A[kk] is multiplied with PG B tiles (alternating k halves) while it stays in the collector
+        const uint64_t dbx = make_desc(sB + (kk ^ 1) * 2 * (N * 16), N * 16, 128);
+#pragma unroll
+        for (int g = 0; g < PG; ++g) {
+          const uint32_t acc = PERF ? 1u : (uint32_t)(it > 0 || kk > 0 || g > 0);
+          const uint64_t dbg = (g & 1) ? dbx : db;
+          if (g == 0) mma_i8_coll<1>(tmem, da, dbg, idesc, acc);
+          else if (g == PG - 1) mma_i8_coll<3>(tmem, da, dbg, idesc, acc);
+          else mma_i8_coll<2>(tmem, da, dbg, idesc, acc);
+        }
       }
     }
     mma_commit(&bar);
@@ -110,7 +146,7 @@ int main() {
   int8_t *dA, *dB; int* dD;
   CK(cudaMalloc(&dA, M * K)); CK(cudaMalloc(&dB, N * K)); CK(cudaMalloc(&dD, sizeof(int) * M * N));
   CK(cudaMemcpy(dA, hA.data(), M * K, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB.data(), N * K, cudaMemcpyHostToDevice));
-  probe<false><<<1, 128>>>(dA, dB, dD, 1);
+  probe<false, false><<<1, 128>>>(dA, dB, dD, 1);
   CK(cudaDeviceSynchronize());
   std::vector<int> hD(M * N);
   CK(cudaMemcpy(hD.data(), dD, sizeof(int) * M * N, cudaMemcpyDeviceToHost));
@@ -121,14 +157,34 @@ int main() {
     if (ref != hD[i * N + j]) { if (bad < 5) printf("mismatch (%d,%d): got %d want %d\n", i, j, hD[i * N + j], ref); ++bad; }
   }
   printf("{\"i8_mma_tile_mismatches\": %ld", bad);
+  // collector run: sum over kk, g of A[:, kk half] * B[:, (kk ^ (g & 1)) half]^T
+  probe<false, true><<<1, 128>>>(dA, dB, dD, 1);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(hD.data(), dD, sizeof(int) * M * N, cudaMemcpyDeviceToHost));
+  long badc = 0;
+  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
+    int ref = 0;
+    for (int kk = 0; kk < 2; ++kk) for (int g = 0; g < PG; ++g) {
+      const int kb = (kk ^ (g & 1)) * 32;
+      for (int k = 0; k < 32; ++k) ref += (int)rA[i * K + kk * 32 + k] * (int)rB[j * K + kb + k];
+    }
+    if (ref != hD[i * N + j]) { if (badc < 5) printf("collector mismatch (%d,%d): got %d want %d\n", i, j, hD[i * N + j], ref); ++badc; }
+  }
+  printf(", \"collector_mismatches\": %ld", badc);
   // throughput: one CTA per SM, back-to-back accumulating MMAs on resident operands
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int iters = 20000;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  probe<true><<<p.multiProcessorCount, 128>>>(dA, dB, dD, 100); CK(cudaDeviceSynchronize());
-  cudaEventRecord(e0); probe<true><<<p.multiProcessorCount, 128>>>(dA, dB, dD, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+  probe<true, false><<<p.multiProcessorCount, 128>>>(dA, dB, dD, 100); CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0); probe<true, false><<<p.multiProcessorCount, 128>>>(dA, dB, dD, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   double ops = 2.0 * M * N * K * (double)iters * p.multiProcessorCount;
-  printf(", \"i8_mma_m128n128_tops\": %.1f, \"ms\": %.3f}\n", ops / ms * 1e-9, ms);
+  printf(", \"n\": %d, \"i8_mma_tops\": %.1f, \"ms\": %.3f", N, ops / ms * 1e-9, ms);
+  iters /= PG;
+  probe<true, true><<<p.multiProcessorCount, 128>>>(dA, dB, dD, 100); CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0); probe<true, true><<<p.multiProcessorCount, 128>>>(dA, dB, dD, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+  cudaEventElapsedTime(&ms, e0, e1);
+  ops = 2.0 * M * N * K * (double)iters * PG * p.multiProcessorCount;
+  printf(", \"collector_group\": %d, \"i8_mma_collector_tops\": %.1f, \"collector_ms\": %.3f}\n", PG, ops / ms * 1e-9, ms);
   return 0;
 }
