@@ -659,7 +659,8 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
     }
     StageTimer t(ctx, ST_POSTERIOR);
     B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * B7_I8_SLICES, gp->sigma + (size_t)s * gp->Np,
-                                    gp->beta + (size_t)s * gp->Np, gp->Np, ksS, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
+                                    gp->beta + (size_t)s * gp->Np, gp->Np, ksS, A, rows, gp->d, gp->Xt, gp->par + (size_t)s * kParStride,
+                                    gp->kernel, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
     t.stop(1);
     return 0;
   }

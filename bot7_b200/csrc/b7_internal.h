@@ -140,6 +140,7 @@ int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, dou
 int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
                      const double* par, double tau, int8_t* ksS);
 int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
+                           const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
                            int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var);
 // score.cu
 int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,

@@ -50,19 +50,30 @@ constexpr int I8_SMEM = NSTAGE * STAGE + RED_BYTES + 1024;   // stages + reducti
 
 // ---- slicing -------------------------------------------------------------------------------------------
 
-// 7 signed digits of t in (-1, 1):  t = sum_p d_p 2^-(8p-2) + O(2^-54), d_1 in [-64, 64], the others radix 256
-// in [-128, 127].  A radix-256 digit set without redundancy only closes if every remainder stays inside
-// [-128/255, 127/255), hence the floor(r + 128/255) rounding; the clamp catches the ulp-wide boundary cases
-// (the excess moves to the next digit and ends below the truncation level).
-__device__ __forceinline__ void digits7(double t, int (&d)[NS]) {
-  double r = t * 64.0;
-#pragma unroll
-  for (int p = 0; p < NS; ++p) {
-    double q = floor(r + (128.0 / 255.0));
-    if (p > 0) q = fmin(fmax(q, -128.0), 127.0);
-    d[p] = (int)q;
-    r = (r - q) * 256.0;
-  }
+// 7 signed digits of t in (-1, 1):  t = sum_p d_p 2^-(8p-2) + O(2^-55), d_1 in [-64, 64], the others radix 256 in
+// [-128, 127].  x = rint(t 2^54) is exact in int64; adding 128 at the six low byte positions turns the balanced
+// digits into the plain bytes of the sum (the carries are the 64-bit add's own), and xor 0x80 maps byte b to
+// the int8 b - 128.  Result: byte k (k = 0..5) = digit 7 - k, bits 48.. = d_1 (its low byte is the int8).
+__device__ __forceinline__ unsigned long long digit_bytes(double t) {
+  const long long x = __double2ll_rn(t * 18014398509481984.0);   // 2^54
+  return (unsigned long long)(x + 0x0000808080808080LL) ^ 0x0000808080808080ULL;
+}
+
+// digit bytes of 4 consecutive k -> one 32-bit word per slice (byte j = element j): two 4 x 4 byte transposes
+__device__ __forceinline__ void pack4(const unsigned long long (&z)[4], uint32_t (&w)[NS]) {
+  const uint32_t l0 = (uint32_t)z[0], l1 = (uint32_t)z[1], l2 = (uint32_t)z[2], l3 = (uint32_t)z[3];
+  const uint32_t h0 = (uint32_t)(z[0] >> 32), h1 = (uint32_t)(z[1] >> 32), h2 = (uint32_t)(z[2] >> 32), h3 = (uint32_t)(z[3] >> 32);
+  const uint32_t la = __byte_perm(l0, l1, 0x5140), lb = __byte_perm(l0, l1, 0x7362);   // [0.b0 1.b0 0.b1 1.b1], [0.b2 1.b2 0.b3 1.b3]
+  const uint32_t lc = __byte_perm(l2, l3, 0x5140), ld = __byte_perm(l2, l3, 0x7362);
+  const uint32_t ha = __byte_perm(h0, h1, 0x5140), hb = __byte_perm(h0, h1, 0x7362);
+  const uint32_t hc = __byte_perm(h2, h3, 0x5140), hd = __byte_perm(h2, h3, 0x7362);
+  w[6] = __byte_perm(la, lc, 0x5410);   // digit 7 = byte 0 of the low words
+  w[5] = __byte_perm(la, lc, 0x7632);
+  w[4] = __byte_perm(lb, ld, 0x5410);
+  w[3] = __byte_perm(lb, ld, 0x7632);
+  w[2] = __byte_perm(ha, hc, 0x5410);   // digit 3 = byte 0 of the high words
+  w[1] = __byte_perm(ha, hc, 0x7632);
+  w[0] = __byte_perm(hb, hd, 0x5410);   // digit 1 = byte 2 of the high words (|d_1| <= 64)
 }
 
 // L^-1 (tiled fp64, lower) -> per-row power-of-two scale sigma and the slice array
@@ -89,21 +100,19 @@ slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np
   sigma[(long long)s * Np + rb * TM + row] = sg;
   int8_t* dst = facS + (long long)s * facS_stride + (long long)rb * KS_ALL * A_STAGE;
   for (int kc = 0; kc < k_end / 16; ++kc) {
-    uint32_t pk[NS][4];
+    uint32_t pk[4][NS];
 #pragma unroll
-    for (int p = 0; p < NS; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+    for (int g = 0; g < 4; ++g) {
+      unsigned long long z[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int d[NS];
-      digits7(src[b7g::elem_off(row, kc * 16 + i)] * inv, d);
-#pragma unroll
-      for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(d[p] & 0xff)) << (8 * (i & 3));
+      for (int i = 0; i < 4; ++i) z[i] = digit_bytes(src[b7g::elem_off(row, kc * 16 + g * 4 + i)] * inv);
+      pack4(z, pk[g]);
     }
     const int ks = kc / KC, kcc = kc % KC;
 #pragma unroll
     for (int p = 0; p < NS; ++p)
       *reinterpret_cast<uint4*>(dst + (long long)ks * A_STAGE + p * (KC * TM * 16) + kcc * (TM * 16) + row * 16) =
-          make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+          make_uint4(pk[0][p], pk[1][p], pk[2][p], pk[3][p]);
   }
 }
 
@@ -129,9 +138,8 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
 #pragma unroll
   for (int i = 0; i < DT; ++i) a[i] = (row < rows && i < d) ? A[row * d + i] : 0.0;
   const double sf2 = par[B7_MAX_DIMS];
-  uint32_t pk[NS][4];
-#pragma unroll
-  for (int p = 0; p < NS; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+  uint32_t pk[4][NS];
+  unsigned long long z[4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int kk = kc * 16 + i, k = kb64 * 64 + kk;
@@ -150,15 +158,13 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
         val = sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp_neg(-s5r, s_tab));
       }
     }
-    int dg[NS];
-    digits7(val * inv_tau, dg);
-#pragma unroll
-    for (int p = 0; p < NS; ++p) pk[p][i >> 2] |= ((uint32_t)(dg[p] & 0xff)) << (8 * (i & 3));
+    z[i & 3] = digit_bytes(val * inv_tau);
+    if ((i & 3) == 3) pack4(z, pk[i >> 2]);
   }
   const int gkc = kb64 * 4 + kc, ks = gkc / KC, kcc = gkc % KC;
   int8_t* dst = ksS + ((long long)ct * KS_ALL + ks) * B_STAGE + kcc * (TN * 16) + c * 16;
 #pragma unroll
-  for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (KC * TN * 16)) = make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (KC * TN * 16)) = make_uint4(pk[0][p], pk[1][p], pk[2][p], pk[3][p]);
 }
 
 // ---- tcgen05 helpers -----------------------------------------------------------------------------------
@@ -227,8 +233,8 @@ __device__ __forceinline__ double lane_transpose_sum(double (&x)[32], int lane) 
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
 posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, const double* __restrict__ beta,
-                    int Np, int NB, const int8_t* __restrict__ ksS, double tau, double sf2, double mconst,
-                    double* __restrict__ mean, double* __restrict__ var) {
+                    int Np, int NB, const int8_t* __restrict__ ksS, const double* __restrict__ cand, long long rows, int d,
+                    const double* __restrict__ Xt, const double* __restrict__ par, int kernel, double tau, double sf2, double mconst, double* __restrict__ mean, double* __restrict__ var) {
   extern __shared__ __align__(1024) uint8_t smem[];
   double* red = reinterpret_cast<double*>(smem + NSTAGE * STAGE);             // [2 parity][4 warps][64 cols][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE + RED_BYTES);
@@ -360,9 +366,20 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
     }
     if (tid < TN) {
       const long long c = (long long)blockIdx.x * TN + tid;
+      // integers cannot carry a NaN: where the K* row of the fp64 path would be NaN (a NaN coordinate, or an infinite
+      // one under Matern: inf * 0), poison the results here.  With finite observations the scaled distance to
+      // the first one decides it for the whole row.
+      double r2 = 0.0;
+      if (c < rows)
+        for (int j = 0; j < d; ++j) {
+          const double t = (cand[c * d + j] - Xt[(long long)j * Np]) * par[j];
+          r2 = fma(t, t, r2);
+        }
+      const bool nan_row = (r2 != r2) || (kernel == B7_KERNEL_MATERN52 && isinf(r2));
+      const double poison = nan_row ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
       const double vv = sf2 - run2;
-      var[c] = vv > 0.0 ? vv : (vv != vv ? vv : 0.0);
-      mean[c] = mconst + run1;
+      var[c] = (vv > 0.0 ? vv : (vv != vv ? vv : 0.0)) + poison;
+      mean[c] = mconst + run1 + poison;
     }
   }
   tc_fence_before();
@@ -406,14 +423,15 @@ int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int
 }
 
 int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
+                           const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
                            int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var) {
   if (!g_attr_i8[ctx->device & 15]) {
     B7_CUDA(cudaFuncSetAttribute(posterior_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     g_attr_i8[ctx->device & 15] = true;
   }
   if (cols_pad <= 0) return 0;
-  posterior_i8_kernel<<<(unsigned)(cols_pad / TN), I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, Np / TM, ksS, tau, sf2, mconst,
-                                                                                      mean, var);
+  posterior_i8_kernel<<<(unsigned)(cols_pad / TN), I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, Np / TM, ksS, cand, rows, d, Xt, par, kernel, tau,
+                                                                                      sf2, mconst, mean, var);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;

@@ -263,7 +263,7 @@ def test_jitter_retry_policy_matches_reference_policy(ctx, oracle, capsys):
 
 
 def test_both_posterior_paths_agree_with_the_oracle(ctx, oracle):
-    # FP64 DMMA tiles vs error-free int8 slices on tcgen05 (36 exact products recombined in fp64): same handle,
+    # FP64 DMMA tiles vs error-free int8 slices on tcgen05 (28 exact products recombined in fp64): same handle,
     # path switched on the fly; both against the oracle and against each other
     Xo, y, hyp, Xc = make_problem(oracle, 900, 6, 3, 12000, 1e-2)
     f = models.GPFactors(Xo, y, hyp)
@@ -292,6 +292,39 @@ def test_both_posterior_paths_agree_with_the_oracle(ctx, oracle):
         assert np.max(np.abs(a[0][s][1] - b[0][s][1])) <= 1e-12 * np.exp(2 * hyp[s, 6])      # variance: 1e-12 sf2
         assert np.max(np.abs(a[0][s][0] - b[0][s][0])) <= 1e-10
     f.free()
+
+
+def test_nonfinite_candidate_poisons_only_its_own_row(ctx, oracle):
+    # integers cannot carry a NaN through the int8 slices: the kernel re-derives which K* rows the fp64 path would
+    # see as NaN (NaN coordinate; infinite coordinate under Matern, inf * 0).  ARD-SE with an infinite coordinate
+    # is a clean k* = 0: prior mean and prior variance.
+    Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 2, 1000, 1e-2)
+    bad = Xc.copy()
+    bad[5, 2] = np.nan
+    bad[70, 0] = np.inf
+    bad[999, 5] = -np.inf
+    keep = ctx.posterior_path()
+    try:
+        for kern, nan_rows, prior_rows in (("ardse", [5], [70, 999]), ("matern52", [5, 70, 999], [])):
+            f = models.GPFactors(Xo, y, hyp, kern)
+            for path in (L.PATH_FP64_DMMA, L.PATH_INT8_OZAKI):
+                ctx.set_posterior_path(path)
+                m0, v0 = f.predict(1, Xc)
+                m1, v1 = f.predict(1, bad)
+                assert np.isnan(m1[nan_rows]).all() and np.isnan(v1[nan_rows]).all()
+                for r_ in prior_rows:
+                    assert m1[r_] == hyp[1, 8] and abs(v1[r_] / np.exp(2 * hyp[1, 6]) - 1) <= 1e-15
+                ok = np.ones(1000, bool)
+                ok[[5, 70, 999]] = False
+                assert np.array_equal(m0[ok], m1[ok]) and np.array_equal(v0[ok], v1[ok])
+                grid = grids.DeviceGrid.from_host(bad)
+                am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+                L.check(L.lib().b7_acq_score(f.handle, grid.handle, L.SCORE_EI, 0.0, 0, -1.0, float(y.min()), None, C.byref(am),
+                                             C.byref(amo), C.byref(best), C.byref(nn)))
+                assert nn.value == len(nan_rows) and am.value - 1 not in nan_rows
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
 
 
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
