@@ -16,6 +16,7 @@ from . import grids as Grids
 from . import models as Models
 from . import parallel
 from . import scores as Scores
+from . import t7
 
 
 class abstract:
@@ -116,7 +117,35 @@ class abstract:
     def nominate(self):
         print("Error: nominate() method not implemented")
 
+    def save(self, path=None):
+        """bots/abstract.lua:234-240: torch.save('demo_<class>.t7', {best=, x=observed, y=responses}), same file format."""
+        best = {k: (np.asarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in self.best.items()}
+        results = {"best": best, "x": self.observed, "y": self.responses}
+        path = path or "demo_%s.t7" % self.__class__.__name__
+        t7.save(path, results)
+        return path
+
     __call__ = run_experiment
+
+
+def cache_from_results(path_or_table, candidates=None):
+    """Turns a result file written by bot:save (here or by the reference) into the `cache` argument of a bot
+    constructor (bots/abstract.lua:19-44): the run resumes with its observations; `candidates`, if given, is
+    the grid to continue on (the reference keeps it in memory only)."""
+    res = t7.load(path_or_table) if isinstance(path_or_table, (str, bytes)) or hasattr(path_or_table, "__fspath__") else path_or_table
+    x, y = res.get("x"), res.get("y")
+    if x is None or y is None:
+        raise ValueError("result table has no observations (x, y)")
+    x = np.array(x, dtype=np.float64, ndmin=2)
+    y = np.array(y, dtype=np.float64)
+    if y.ndim == 1:
+        y = y.reshape(-1, 1)
+    if x.shape[0] != y.shape[0]:
+        raise ValueError("result table: %d observed points but %d responses" % (x.shape[0], y.shape[0]))
+    cache = {"observed": x, "responses": y}
+    if candidates is not None:
+        cache["candidates"] = candidates
+    return cache
 
 
 class random_search(abstract):

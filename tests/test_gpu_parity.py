@@ -608,3 +608,24 @@ def test_bayesopt_loop_branin(ctx, oracle):
     ref = oracle.acquisition(bot.observed, bot.responses[:, 0], hyps, bot.candidates, 0, False, oracle.SCORE_EI)
     assert score.shape == (5000 - 12,) and idx == ref["idx"]
     assert rel(score, ref["score"], 1e-6 * ref["score"].max()) <= 1e-7
+
+
+def test_bot_save_and_resume_through_the_t7_result_file(ctx, oracle, tmp_path):
+    # bots/abstract.lua:234-240 (save) + :19-44 (cache protocol): a run persisted in Torch7 format resumes with its
+    # observations, on the candidates that were still live, and then behaves like the uninterrupted run's state
+    from bot7_b200 import t7
+    hypers = [{"name": "x1", "size": 1, "min": 0.0, "max": 1.0}, {"name": "x2", "size": 1, "min": 0.0, "max": 1.0}]
+    cfg = {"bot": {"budget": 6, "nInitial": 3, "nSamples": 2, "verbose": 0}, "grid": {"size": 2000}}
+    bot = bots.bayesopt(lambda x: oracle.braninhoo(x)[0], hypers, cfg, rng=np.random.default_rng(5))
+    bot.run_experiment()
+    path = bot.save(str(tmp_path / "demo_bayesopt.t7"))
+    res = t7.load(path)
+    assert list(res) == ["best", "x", "y"] and np.array_equal(res["x"], bot.observed) and np.array_equal(res["y"], bot.responses)
+    assert res["best"]["t"] == bot.best["t"] and np.array_equal(res["best"]["y"], bot.best["y"])
+    cache = bots.cache_from_results(path, candidates=bot.candidates)
+    again = bots.bayesopt(lambda x: oracle.braninhoo(x)[0], hypers, cfg, cache=cache, rng=np.random.default_rng(6))
+    assert again.nTrials == 6 and again.grid.size() == 2000 - 6
+    assert again.best["y"].item() == bot.responses.min() and again.best["t"] == int(bot.responses[:, 0].argmin()) + 1
+    x, y = again.run_trial()
+    assert again.nTrials == 7 and again.observed.shape == (7, 2) and np.array_equal(again.observed[:6], bot.observed)
+    assert not any(np.array_equal(x[0], o) for o in bot.observed)              # a fresh grid row, not a repeat
