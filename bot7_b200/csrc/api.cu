@@ -181,6 +181,7 @@ int b7_init(int device, b7_ctx** out) {
   unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
   B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
+  { const char* e = getenv("B7_POTRF_I8"); ctx->potrf_i8 = !(e && e[0] == '0'); }
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));

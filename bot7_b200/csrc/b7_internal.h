@@ -41,6 +41,7 @@ struct b7_ctx {
   int64_t stage_calls[ST_COUNT] = {0};
   bool profiling = false;
   bool use_i8 = false;           // B7_POSTERIOR_I8=1: posterior pass on the INT8 tensor pipe (posterior_i8.cu)
+  bool potrf_i8 = true;          // with use_i8: also the k = 512 trailing updates of the Cholesky (B7_POTRF_I8=0: FP64 DMMA)
   int64_t launches = 0;
   // scratch for the posterior pass (grown on demand)
   double* ks = nullptr;        // K* panel, [panel_rows][Np]
@@ -133,6 +134,12 @@ int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
 int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out /* N x N row-major */, int Np, int N);
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
                         int64_t cols_pad, double sf2, double mconst, double* mean, double* var);
+// potrf_i8.cu: k = 512 trailing updates of the Cholesky on the INT8 tensor pipe (scratch indexed by position in the batch)
+size_t b7_i8_panel_bytes(int Np, int W);
+int b7_i8_panel_slice(b7_ctx* ctx, cudaStream_t st, const double* fac, int Np, int kb0, int kb1, int row0_blk, int8_t* pA, int8_t* pB,
+                      size_t p_stride, double* sig, int s0, int count);
+int b7_i8_trail(b7_ctx* ctx, cudaStream_t st, double* fac, int Np, const int8_t* pA, const int8_t* pB, size_t p_stride, const double* sig,
+                int kb0, int kb1, int row0_blk, int it0, int n_it, int nt0, int n_nt, int s0, int count);
 // posterior_i8.cu
 #define B7_I8_SLICES 7        // radix-256 digit slices per operand
 #define B7_I8_MAX_NP 16384    // 7 products x 2^14 x Np must stay below 2^31

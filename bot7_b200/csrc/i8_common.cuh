@@ -1,0 +1,87 @@
+// Shared pieces of the INT8 (error-free sliced) tensor paths: digit extraction and the tcgen05 wrappers used by
+// posterior_i8.cu and potrf_i8.cu.
+#pragma once
+#include <stdint.h>
+
+#include "b7_internal.h"
+#include "gemm_tile.cuh"
+
+namespace b7i8 {
+
+using b7g::smem_u32;
+constexpr int NS = B7_I8_SLICES;           // slices per operand (7)
+
+// 7 signed digits of t in (-1, 1):  t = sum_p d_p 2^-(8p-2) + O(2^-55), d_1 in [-64, 64], the others radix 256 in
+// [-128, 127].  x = rint(t 2^54) is exact in int64; adding 128 at the six low byte positions turns the balanced
+// digits into the plain bytes of the sum (the carries are the 64-bit add's own), and xor 0x80 maps byte b to
+// the int8 b - 128.  Result: byte k (k = 0..5) = digit 7 - k, bits 48.. = d_1 (its low byte is the int8).
+__device__ __forceinline__ unsigned long long digit_bytes(double t) {
+  const long long x = __double2ll_rn(t * 18014398509481984.0);   // 2^54
+  return (unsigned long long)(x + 0x0000808080808080LL) ^ 0x0000808080808080ULL;
+}
+
+// digit bytes of 4 consecutive k -> one 32-bit word per slice (byte j = element j): two 4 x 4 byte transposes
+__device__ __forceinline__ void pack4(const unsigned long long (&z)[4], uint32_t (&w)[NS]) {
+  const uint32_t l0 = (uint32_t)z[0], l1 = (uint32_t)z[1], l2 = (uint32_t)z[2], l3 = (uint32_t)z[3];
+  const uint32_t h0 = (uint32_t)(z[0] >> 32), h1 = (uint32_t)(z[1] >> 32), h2 = (uint32_t)(z[2] >> 32), h3 = (uint32_t)(z[3] >> 32);
+  const uint32_t la = __byte_perm(l0, l1, 0x5140), lb = __byte_perm(l0, l1, 0x7362);   // [0.b0 1.b0 0.b1 1.b1], [0.b2 1.b2 0.b3 1.b3]
+  const uint32_t lc = __byte_perm(l2, l3, 0x5140), ld = __byte_perm(l2, l3, 0x7362);
+  const uint32_t ha = __byte_perm(h0, h1, 0x5140), hb = __byte_perm(h0, h1, 0x7362);
+  const uint32_t hc = __byte_perm(h2, h3, 0x5140), hd = __byte_perm(h2, h3, 0x7362);
+  w[6] = __byte_perm(la, lc, 0x5410);   // digit 7 = byte 0 of the low words
+  w[5] = __byte_perm(la, lc, 0x7632);
+  w[4] = __byte_perm(lb, ld, 0x5410);
+  w[3] = __byte_perm(lb, ld, 0x7632);
+  w[2] = __byte_perm(ha, hc, 0x5410);   // digit 3 = byte 0 of the high words
+  w[1] = __byte_perm(ha, hc, 0x7632);
+  w[0] = __byte_perm(hb, hd, 0x5410);   // digit 1 = byte 2 of the high words (|d_1| <= 64)
+}
+
+// ---- tcgen05 helpers -----------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t umma_desc(const void* smem, int lbo_bytes, int sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // K-direction stride between 16-byte chunks
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // M/N-direction stride between 8-row groups
+  d |= (uint64_t)1 << 46;                             // sm_100 descriptor version; SWIZZLE_NONE
+  return d;
+}
+// HINT: 0 = plain, 1 = keep A in the collector (fill), 2 = A from the collector and keep it (use),
+// 3 = A from the collector, then release it (lastuse).  SASS: UTCIMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE
+template <int HINT>
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+#define B7_UMMA_I8(QUAL)                                                                                            \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t}\n" \
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory")
+  if (HINT == 1) B7_UMMA_I8(".collector::a::fill");
+  else if (HINT == 2) B7_UMMA_I8(".collector::a::use");
+  else if (HINT == 3) B7_UMMA_I8(".collector::a::lastuse");
+  else B7_UMMA_I8("");
+#undef B7_UMMA_I8
+}
+// one lane of a converged warp (all 32 lanes must call it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+}  // namespace b7i8

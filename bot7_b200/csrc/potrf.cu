@@ -392,6 +392,21 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   const int W = W_env > 0 ? W_env : 4;   // outer panel = 4 blocks (512 columns)
   cudaStream_t sa = ctx->stream, sb = ctx->stream2;
   bool far_pending = false;
+  // INT8 path (potrf_i8.cu): the panel rows are sliced once per outer panel into one of two scratch sets (the far
+  // update of panel J still reads its set while panel J + W is sliced)
+  // (batched fits only: a single factor is a latency chain that the extra slicing launch makes longer; measured
+  // at N = 4096: S = 32 26.7 -> 17.7 ms, S = 1 4.1 -> 4.8 ms)
+  const bool i8 = ctx->use_i8 && ctx->potrf_i8 && count >= 4 && NB > W && Np <= B7_I8_MAX_NP;
+  int8_t* pS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  double* pSig[2] = {nullptr, nullptr};
+  const size_t p_stride = i8 ? b7_i8_panel_bytes(Np, W) : 0;
+  if (i8)
+    for (int b = 0; b < 2; ++b) {
+      B7_CHECK(b7_pool_alloc(ctx, (void**)&pS[b][0], p_stride * count));
+      B7_CHECK(b7_pool_alloc(ctx, (void**)&pS[b][1], p_stride * count));
+      B7_CHECK(b7_pool_alloc(ctx, (void**)&pSig[b], sizeof(double) * (size_t)Np * count));
+    }
+  int set = 0;
   for (int J = 0; J < NB; J += W) {
     const int Jend = J + W < NB ? J + W : NB;
     // --- the panel's own columns: latency-bound chain on the main stream ---
@@ -414,19 +429,37 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
     //     (after the previous far update, which touched the same tiles).  "far": everything to the right of
     //     the next panel, on the second stream, overlapping the next panel's chain of small kernels. ---
     const int near_end = Jend + W < NB ? Jend + W : NB;
+    if (i8) B7_CHECK(b7_i8_panel_slice(ctx, sa, gp->fac, Np, J, Jend, Jend, pS[set][0], pS[set][1], p_stride, pSig[set], s0, count));
     if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
-    trail_kernel<<<dim3(NB - Jend, near_end - Jend, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
-    b7_count(ctx);
+    if (i8) {
+      B7_CHECK(b7_i8_trail(ctx, sa, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, Jend, NB - Jend, Jend,
+                           near_end - Jend, s0, count));
+    } else {
+      trail_kernel<<<dim3(NB - Jend, near_end - Jend, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
+      b7_count(ctx);
+    }
     if (near_end < NB) {
       B7_CUDA(cudaEventRecord(ctx->evA, sa));
       B7_CUDA(cudaStreamWaitEvent(sb, ctx->evA, 0));
-      trail_kernel<<<dim3(NB - near_end, NB - near_end, count), THREADS, RING_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
-      b7_count(ctx);
+      if (i8) {
+        B7_CHECK(b7_i8_trail(ctx, sb, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, near_end, NB - near_end,
+                             near_end, NB - near_end, s0, count));
+      } else {
+        trail_kernel<<<dim3(NB - near_end, NB - near_end, count), THREADS, RING_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
+        b7_count(ctx);
+      }
       B7_CUDA(cudaEventRecord(ctx->evB, sb));
       far_pending = true;
     }
+    set ^= 1;
   }
   if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+  if (i8)
+    for (int b = 0; b < 2; ++b) {
+      b7_pool_free(ctx, pS[b][0]);
+      b7_pool_free(ctx, pS[b][1]);
+      b7_pool_free(ctx, pSig[b]);
+    }
   B7_CUDA(cudaGetLastError());
   return 0;
 }

@@ -73,6 +73,13 @@ class GPFactors:
         L.check(L.lib().b7_gp_predict(self.handle, int(s), L.dptr(Xs), M, L.dptr(mean), L.dptr(var)), "b7_gp_predict")
         return mean, var
 
+    def read_factor(self, s):
+        """Lower triangle of draw s's factor as an N x N array: L after a fit without inversion (FIT_LOGML_ONLY /
+        FIT_DEFER), L^-1 once the handle can predict."""
+        out = np.empty((self.N, self.N))
+        L.check(L.lib().b7_gp_read_factor(self.handle, int(s), L.dptr(out)), "b7_gp_read_factor")
+        return np.tril(out)
+
     def padded_n(self):
         return int(L.lib().b7_gp_padded_n(self.handle))
 

@@ -327,6 +327,32 @@ def test_nonfinite_candidate_poisons_only_its_own_row(ctx, oracle):
         ctx.set_posterior_path(keep)
 
 
+def test_int8_trailing_update_of_the_cholesky_matches_the_fp64_one(ctx, oracle):
+    # potrf_i8.cu: with the INT8 path selected, batched fits (>= 4 draws, more than one outer panel) run the k = 512
+    # trailing updates as exact int8 slice products; the factor must agree with the all-FP64 factorisation to
+    # rounding level, and both with the oracle
+    Xo, y, hyp, _ = make_problem(oracle, 1500, 6, 5, 10, 1e-3)
+    keep = ctx.posterior_path()
+    out = {}
+    try:
+        for path in (L.PATH_FP64_DMMA, L.PATH_INT8_OZAKI):
+            ctx.set_posterior_path(path)
+            f = models.GPFactors(Xo, y, hyp, flags=L.FIT_LOGML_ONLY)
+            assert (np.asarray(f.info) == 0).all()
+            out[path] = (np.array(f.logml), [f.read_factor(s) for s in (0, 4)])
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
+    a, b = out[L.PATH_FP64_DMMA], out[L.PATH_INT8_OZAKI]
+    assert rel(a[0], b[0], 1e-300) <= 1e-12
+    for La, Lb, s in zip(a[1], b[1], (0, 4)):
+        assert np.max(np.abs(La - Lb)) <= 1e-12 * np.max(np.abs(La))
+        assert not np.array_equal(La, Lb)                                # the two arithmetic paths really differ
+        ref = oracle.gp_fit(Xo, y, hyp[s], 0)
+        assert np.max(np.abs(Lb - np.tril(ref["L"]))) <= 1e-10 * np.max(np.abs(ref["L"]))
+        assert rel(b[0][s:s + 1], np.array([ref["logml"]]), 1e-300) <= 1e-11
+
+
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
     Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 3, 2000, 1e-2)
     a = models.GPFactors(Xo, y, hyp)
