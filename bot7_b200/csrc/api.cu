@@ -182,6 +182,7 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_POTRF_I8"); ctx->potrf_i8 = !(e && e[0] == '0'); }
+  { const char* e = getenv("B7_TRTRI_I8"); ctx->trtri_i8 = !(e && e[0] == '0'); }
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));

@@ -42,6 +42,7 @@ struct b7_ctx {
   bool profiling = false;
   bool use_i8 = false;           // B7_POSTERIOR_I8=1: posterior pass on the INT8 tensor pipe (posterior_i8.cu)
   bool potrf_i8 = true;          // with use_i8: also the k = 512 trailing updates of the Cholesky (B7_POTRF_I8=0: FP64 DMMA)
+  bool trtri_i8 = true;          // with use_i8: also the inversion of the factors (B7_TRTRI_I8=0: FP64 DMMA sweep)
   int64_t launches = 0;
   // scratch for the posterior pass (grown on demand)
   double* ks = nullptr;        // K* panel, [panel_rows][Np]
@@ -140,6 +141,8 @@ int b7_i8_panel_slice(b7_ctx* ctx, cudaStream_t st, const double* fac, int Np, i
                       size_t p_stride, double* sig, int s0, int count);
 int b7_i8_trail(b7_ctx* ctx, cudaStream_t st, double* fac, int Np, const int8_t* pA, const int8_t* pB, size_t p_stride, const double* sig,
                 int kb0, int kb1, int row0_blk, int it0, int n_it, int nt0, int n_nt, int s0, int count);
+// trtri_i8.cu: L -> L^-1 by block-recursive int8 products (the diagonal tiles must already hold their inverses)
+int b7_launch_trtri_i8(b7_gp* gp, int s0, int count);
 // posterior_i8.cu
 #define B7_I8_SLICES 7        // radix-256 digit slices per operand
 #define B7_I8_MAX_NP 16384    // 7 products x 2^14 x Np must stay below 2^31

@@ -1,5 +1,5 @@
 // Shared pieces of the INT8 (error-free sliced) tensor paths: digit extraction and the tcgen05 wrappers used by
-// posterior_i8.cu and potrf_i8.cu.
+// posterior_i8.cu, potrf_i8.cu and trtri_i8.cu.
 #pragma once
 #include <stdint.h>
 
@@ -83,5 +83,64 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
       : "r"(addr));
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+
+// ---- the 128 x 64 x 64 stage shared by the factorisation kernels (potrf_i8.cu, trtri_i8.cu) ----------------
+// A stage = 7 slices x 128 rows x 64 k-bytes of the row operand followed by 7 x 64 x 64 of the column operand, both
+// in the UMMA canonical K-major no-swizzle layout [slice][16-byte k chunk][row][16].
+namespace gemm {
+constexpr int TM = 128, TN = 64, KB = 64, KC = KB / 16;
+constexpr int A_STAGE = NS * TM * KB;      // 57344 B
+constexpr int B_STAGE = NS * TN * KB;      // 28672 B
+constexpr int STAGE = A_STAGE + B_STAGE;   // 86016 B
+constexpr int NSTAGE = 2;
+constexpr int THREADS = 192;               // warps 0-3 epilogue, 4 producer, 5 MMA issue
+constexpr int SMEM = NSTAGE * STAGE + 1024;
+
+// instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+__device__ __forceinline__ uint32_t idesc_128x64() {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// the 56 MMAs of one stage (call from ONE elected lane): slice p of the row operand meets slices 1 .. 8 - p of the
+// column operand from the collector; class p + q accumulates in TMEM columns (p + q - 2) * 64
+__device__ __forceinline__ void mma_stage(const uint8_t* stage, uint32_t tmem, uint32_t idesc, bool first) {
+  const uint64_t da0 = umma_desc(stage, TM * 16, 128), db0 = umma_desc(stage + A_STAGE, TN * 16, 128);
+#pragma unroll
+  for (int k2 = 0; k2 < KB / 32; ++k2) {
+#pragma unroll
+    for (int p = 1; p <= NS; ++p) {
+      const uint64_t da = da0 + (uint64_t)(((p - 1) * (KC * TM * 16) + k2 * (2 * TM * 16)) >> 4);
+      const uint32_t acc = (first && k2 == 0 && p == 1) ? 0u : 1u;
+      const int nq = NS + 1 - p;
+#pragma unroll
+      for (int q = 1; q <= nq; ++q) {
+        const uint64_t db = db0 + (uint64_t)(((q - 1) * (KC * TN * 16) + k2 * (2 * TN * 16)) >> 4);
+        const uint32_t dcol = tmem + (uint32_t)((p + q - 2) * TN);
+        if (nq == 1) umma_i8<0>(dcol, da, db, idesc, acc);
+        else if (q == 1) umma_i8<1>(dcol, da, db, idesc, acc);
+        else if (q == nq) umma_i8<3>(dcol, da, db, idesc, acc);
+        else umma_i8<2>(dcol, da, db, idesc, acc);
+      }
+    }
+  }
+}
+
+// epilogue warp `warp` (0-3), thread = TMEM lane: v[c] = sum_w 2^(4-8w) S_w[lane][c] for the 64 columns
+__device__ __forceinline__ void drain_classes(uint32_t tmem, int warp, double (&v)[TN]) {
+#pragma unroll
+  for (int c = 0; c < TN; ++c) v[c] = 0.0;
+#pragma unroll
+  for (int wc = 2; wc <= NS + 1; ++wc) {
+    const double wt = ldexp(1.0, 4 - 8 * wc);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t dv[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((wc - 2) * TN + hh * 32), dv);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[hh * 32 + c] = fma((double)(int)dv[c], wt, v[hh * 32 + c]);
+    }
+  }
+}
+}  // namespace gemm
 
 }  // namespace b7i8

@@ -478,6 +478,8 @@ int b7_launch_trtri(b7_gp* gp, int s0, int count) {
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK, ts = (long long)NBK * Np;
   place_diag_kernel<<<dim3(NB, count), 256, 0, ctx->stream>>>(gp->fac, fs, Np, gp->dinv, ds, s0);
   b7_count(ctx);
+  // INT8 path: block-recursive inversion with static operands per level (trtri_i8.cu)
+  if (ctx->use_i8 && ctx->trtri_i8 && Np <= B7_I8_MAX_NP) return b7_launch_trtri_i8(gp, s0, count);
   for (int j = NB - 2; j >= 0; --j) {
     const int rem = NB - 1 - j;
     inv_step1_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, ctx->stream>>>(gp->fac, fs, Np, j, gp->dinvT, ds, gp->tt, ts, s0);
