@@ -50,8 +50,11 @@ int  b7_last_stage_ms(b7_ctx* ctx, int stage, double* ms_total, int64_t* launche
  *   B7_PATH_FP64_DMMA  fp64 operands on DMMA tiles (posterior.cu);
  *   B7_PATH_INT8_OZAKI both operands split error-free into 7 radix-256 int8 slices, 28 exact int32 products on
  *                      tcgen05.mma.kind::i8, recombined in fp64 (posterior_i8.cu): same results to ~5e-14 sf2,
- *                      2.6x the throughput.  Default; B7_POSTERIOR_I8=0 in the environment selects DMMA; fits with
- *                      more than 16384 observations always use DMMA (int32 exactness bound). */
+ *                      2.6x the throughput.  With this path the k = 512 trailing updates of batched factorisations
+ *                      (potrf_i8.cu) and the inversion of the factors (trtri_i8.cu) use the same slicing
+ *                      (B7_POTRF_I8=0 / B7_TRTRI_I8=0 keep those in FP64).  Default; B7_POSTERIOR_I8=0 in the
+ *                      environment selects DMMA; fits with more than 16384 observations always use DMMA (int32
+ *                      exactness bound). */
 enum { B7_PATH_FP64_DMMA = 0, B7_PATH_INT8_OZAKI = 1 };
 int  b7_set_posterior_path(b7_ctx* ctx, int path);
 int  b7_get_posterior_path(b7_ctx* ctx);
