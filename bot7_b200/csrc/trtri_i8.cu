@@ -271,25 +271,36 @@ int launch_gemm(b7_ctx* ctx, const int8_t* sA, long long sA_draw, const int8_t* 
 }  // namespace
 
 // L -> L^-1 in place for draws [s0, s0 + count); the diagonal tiles must already hold the 128 x 128 inverses
+static int trtri_i8_group(b7_gp* gp, int s0, int count, size_t rows_max, size_t w_max);
+
 int b7_launch_trtri_i8(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
-  const int Np = gp->Np, NB = gp->NB;
+  const int NB = gp->NB;
   if (NB < 2) return 0;
   if (!g_attr[ctx->device & 15]) {
     B7_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     g_attr[ctx->device & 15] = true;
   }
-  int nb_top = 1;
-  while (nb_top * 2 < NB) nb_top *= 2;                     // largest level
-  const int pairs_top = (NB + 2 * nb_top - 1) / (2 * nb_top);
-  // scratch, sized for the level that needs most: slices (pairs * nb row blocks x 2 nb stages), W, scales
+  // scratch per draw, sized for the level that needs most: slices (pairs * nb row blocks x 2 nb stages), W, scales
   size_t rows_max = 0, w_max = 0;
   for (int nb = 1; nb < NB; nb *= 2) {
     const size_t pairs = (size_t)(NB + 2 * nb - 1) / (2 * nb);
     rows_max = rows_max > pairs * nb * 2 * nb ? rows_max : pairs * nb * 2 * nb;
     w_max = w_max > pairs * nb * nb ? w_max : pairs * nb * nb;
   }
-  (void)pairs_top;
+  // draws are processed in groups so that the scratch stays below ~6 GB whatever N and S are
+  const size_t per_draw = rows_max * (A_STAGE + 2 * B_STAGE) + w_max * 128 * 128 * sizeof(double);
+  const size_t budget = (size_t)6 << 30;
+  int group = (int)(budget / per_draw);
+  group = group < 1 ? 1 : (group > count ? count : group);
+  for (int g0 = 0; g0 < count; g0 += group)
+    B7_CHECK(trtri_i8_group(gp, s0 + g0, count - g0 < group ? count - g0 : group, rows_max, w_max));
+  return 0;
+}
+
+static int trtri_i8_group(b7_gp* gp, int s0, int count, size_t rows_max, size_t w_max) {
+  b7_ctx* ctx = gp->ctx;
+  const int Np = gp->Np, NB = gp->NB;
   const size_t sA_draw = rows_max * A_STAGE, sB_draw = rows_max * 2 * B_STAGE, w_draw = w_max * 128 * 128, sig_draw = (size_t)Np;
   int8_t *sA = nullptr, *sB = nullptr;
   double *W = nullptr, *sigA = nullptr, *sigB = nullptr;

@@ -353,6 +353,31 @@ def test_int8_trailing_update_of_the_cholesky_matches_the_fp64_one(ctx, oracle):
         assert rel(b[0][s:s + 1], np.array([ref["logml"]]), 1e-300) <= 1e-11
 
 
+@pytest.mark.parametrize("N,S", [(300, 2), (600, 2), (1700, 1), (2304, 4)])
+def test_block_recursive_int8_inverse_matches_the_fp64_sweep(ctx, oracle, N, S):
+    # trtri_i8.cu: X21 = -X22 (L21 X11) per level with exact int8 slice products; 3, 5, 14 and 18 row blocks leave the
+    # last pair of a level short or empty at different levels.  Against the FP64 column sweep and against numpy.
+    Xo, y, hyp, _ = make_problem(oracle, N, 6, S, 10, 1e-3)
+    keep = ctx.posterior_path()
+    out = {}
+    try:
+        for path in (L.PATH_FP64_DMMA, L.PATH_INT8_OZAKI):
+            ctx.set_posterior_path(path)
+            f = models.GPFactors(Xo, y, hyp)
+            assert (np.asarray(f.info) == 0).all()
+            out[path] = [f.read_factor(s) for s in range(S)]
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
+    for s in range(S):
+        a, b = out[L.PATH_FP64_DMMA][s], out[L.PATH_INT8_OZAKI][s]
+        scale = np.max(np.abs(a))
+        assert np.max(np.abs(a - b)) <= 1e-11 * scale
+        assert N <= 128 or not np.array_equal(a, b)
+        ref = np.linalg.inv(np.tril(oracle.gp_fit(Xo, y, hyp[s], 0)["L"]))
+        assert np.max(np.abs(b - np.tril(ref))) <= 1e-9 * scale
+
+
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
     Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 3, 2000, 1e-2)
     a = models.GPFactors(Xo, y, hyp)
