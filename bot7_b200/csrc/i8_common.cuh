@@ -84,6 +84,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// ---- slicing kernels: 512 threads = 128 rows (or columns) x 4 interleaved k quarters --------------------------
+constexpr int SLICE_THREADS = 512;
+
+// power-of-two scale of one row from the partial maxima of its four quarters (NaN when any entry was not finite:
+// a failed pivot must poison what it touches, as it does on the fp64 path).  s_red: 512 doubles of shared memory.
+__device__ __forceinline__ double row_scale(double mx, bool bad, double* s_red, int row, int q) {
+  s_red[q * 128 + row] = bad ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+  __syncthreads();
+  double m = 0.0;
+  bool b = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double v = s_red[j * 128 + row];
+    b |= (v != v);
+    m = fmax(m, v);
+  }
+  int e = 0;
+  frexp(m, &e);                                    // 2^e > m
+  return b ? __longlong_as_double(0x7ff8000000000000LL) : (m > 0.0 ? ldexp(1.0, e) : 1.0);
+}
+
+// 16 consecutive entries of one row in the tiled fp64 layout (p points at elem_off(row, 16 c)): max / digits
+__device__ __forceinline__ void chunk_max(const double* p, double& mx, bool& bad) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const double4 v = *reinterpret_cast<const double4*>(p + g * (128 * 4));
+    bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    mx = fmax(mx, fmax(fmax(fabs(v.x), fabs(v.y)), fmax(fabs(v.z), fabs(v.w))));
+  }
+}
+__device__ __forceinline__ void chunk_digits(const double* p, double inv, uint32_t (&pk)[4][NS]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const double4 v = *reinterpret_cast<const double4*>(p + g * (128 * 4));
+    const unsigned long long z[4] = {digit_bytes(v.x * inv), digit_bytes(v.y * inv), digit_bytes(v.z * inv), digit_bytes(v.w * inv)};
+    pack4(z, pk[g]);
+  }
+}
+
 // ---- the 128 x 64 x 64 stage shared by the factorisation kernels (potrf_i8.cu, trtri_i8.cu) ----------------
 // A stage = 7 slices x 128 rows x 64 k-bytes of the row operand followed by 7 x 64 x 64 of the column operand, both
 // in the UMMA canonical K-major no-swizzle layout [slice][16-byte k chunk][row][16].

@@ -53,36 +53,24 @@ constexpr int I8_SMEM = NSTAGE * STAGE + RED_BYTES + 1024;   // stages + reducti
 
 // L^-1 (tiled fp64, lower) -> per-row power-of-two scale sigma and the slice array
 // facS[rb][ks][p][kc][row][16]  (ks = KB-column stage, kc = 16-column chunk inside it)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SLICE_THREADS)
 slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np, int8_t* __restrict__ facS,
                     long long facS_stride, double* __restrict__ sigma, int s0) {
-  const int rb = blockIdx.x, s = s0 + blockIdx.y, row = threadIdx.x;
-  const int KTA = Np / 16, KS_ALL = Np / KB;
+  __shared__ double s_red[SLICE_THREADS];
+  const int rb = blockIdx.x, s = s0 + blockIdx.y, row = threadIdx.x & 127, q = threadIdx.x >> 7;
+  const int KTA = Np / 16, KS_ALL = Np / KB, n_kc = (rb + 1) * (TM / 16);
   const double* src = fac + (long long)s * fac_stride + b7g::tile_off(KTA, rb, 0);
-  const int k_end = (rb + 1) * TM;
   double mx = 0.0;
   bool bad = false;
-  for (int k4 = 0; k4 < k_end; k4 += 4) {
-    const double* p = src + b7g::elem_off(row, k4);
-    bad |= !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]));
-    mx = fmax(mx, fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3]))));
-  }
-  int e = 0;
-  frexp(mx, &e);                                   // mx = f 2^e, f in [0.5, 1)  ->  2^e > mx
+  for (int kc = q; kc < n_kc; kc += 4) chunk_max(src + b7g::elem_off(row, kc * 16), mx, bad);
   // a failed factorisation (NaN / inf in the row) must poison the results like it does on the fp64 path
-  const double sg = bad ? __longlong_as_double(0x7ff8000000000000LL) : (mx > 0.0 ? ldexp(1.0, e) : 1.0);
-  const double inv = bad ? 0.0 : 1.0 / sg;
-  sigma[(long long)s * Np + rb * TM + row] = sg;
+  const double sg = row_scale(mx, bad, s_red, row, q);
+  const double inv = sg != sg ? 0.0 : 1.0 / sg;
+  if (q == 0) sigma[(long long)s * Np + rb * TM + row] = sg;
   int8_t* dst = facS + (long long)s * facS_stride + (long long)rb * KS_ALL * A_STAGE;
-  for (int kc = 0; kc < k_end / 16; ++kc) {
+  for (int kc = q; kc < n_kc; kc += 4) {
     uint32_t pk[4][NS];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      unsigned long long z[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) z[i] = digit_bytes(src[b7g::elem_off(row, kc * 16 + g * 4 + i)] * inv);
-      pack4(z, pk[g]);
-    }
+    chunk_digits(src + b7g::elem_off(row, kc * 16), inv, pk);
     const int ks = kc / KC, kcc = kc % KC;
 #pragma unroll
     for (int p = 0; p < NS; ++p)
@@ -320,7 +308,7 @@ bool g_attr_i8[16] = {false};
 }  // namespace
 
 int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count) {
-  slice_factor_kernel<<<dim3(Np / TM, count), 128, 0, ctx->stream>>>(fac, (long long)Np * Np, Np, facS, (long long)Np * Np * NS, sigma, s0);
+  slice_factor_kernel<<<dim3(Np / TM, count), SLICE_THREADS, 0, ctx->stream>>>(fac, (long long)Np * Np, Np, facS, (long long)Np * Np * NS, sigma, s0);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;

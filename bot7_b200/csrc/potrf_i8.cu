@@ -39,37 +39,24 @@ constexpr int T_SMEM = NSTAGE * STAGE + 1024;
 
 // rows [row0_blk*128, Np) of the panel columns [k0, k0 + n_ks*64): per-row scale and slices in both layouts
 //   pA[rb - row0_blk][ks][p][kc][128 rows][16]      pB[(rb - row0_blk) * 2 + half][ks][p][kc][64 rows][16]
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SLICE_THREADS)
 slice_panel_kernel(const double* __restrict__ fac, long long fac_stride, int Np, int kb0, int n_ks, int row0_blk,
                    int8_t* __restrict__ pA, int8_t* __restrict__ pB, long long p_stride, double* __restrict__ sig, int s0) {
-  const int rb = row0_blk + blockIdx.x, s = s0 + blockIdx.y, row = threadIdx.x;
-  const int KTA = Np / 16;
+  __shared__ double s_red[SLICE_THREADS];
+  const int rb = row0_blk + blockIdx.x, s = s0 + blockIdx.y, row = threadIdx.x & 127, q = threadIdx.x >> 7;
+  const int KTA = Np / 16, n_kc = n_ks * KC;
   const double* src = fac + (long long)s * fac_stride + tile_off(KTA, rb, kb0 * (128 / 16));
-  const int kw = n_ks * KB;
   double mx = 0.0;
   bool bad = false;
-  for (int k4 = 0; k4 < kw; k4 += 4) {
-    const double* p = src + elem_off(row, k4);
-    bad |= !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]));
-    mx = fmax(mx, fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3]))));
-  }
-  int e = 0;
-  frexp(mx, &e);                                   // 2^e > mx
-  // a non-finite panel row (failed pivot) must poison what it updates, as it does on the fp64 path
-  const double sg = bad ? __longlong_as_double(0x7ff8000000000000LL) : (mx > 0.0 ? ldexp(1.0, e) : 1.0);
-  const double inv = bad ? 0.0 : 1.0 / sg;
-  sig[(long long)blockIdx.y * Np + rb * TM + row] = sg;           // scratch is indexed by the draw's position in the batch
+  for (int kc = q; kc < n_kc; kc += 4) chunk_max(src + elem_off(row, kc * 16), mx, bad);
+  const double sg = row_scale(mx, bad, s_red, row, q);
+  const double inv = sg != sg ? 0.0 : 1.0 / sg;
+  if (q == 0) sig[(long long)blockIdx.y * Np + rb * TM + row] = sg;   // scratch is indexed by the draw's position in the batch
   int8_t* dA = pA + (long long)blockIdx.y * p_stride + (long long)blockIdx.x * n_ks * A_STAGE;
   int8_t* dB = pB + (long long)blockIdx.y * p_stride + (long long)(blockIdx.x * 2 + (row >> 6)) * n_ks * B_STAGE;
-  for (int kc = 0; kc < kw / 16; ++kc) {
+  for (int kc = q; kc < n_kc; kc += 4) {
     uint32_t pk[4][NS];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      unsigned long long z[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) z[i] = digit_bytes(src[elem_off(row, kc * 16 + g * 4 + i)] * inv);
-      pack4(z, pk[g]);
-    }
+    chunk_digits(src + elem_off(row, kc * 16), inv, pk);
     const int ks = kc / KC, kcc = kc % KC;
 #pragma unroll
     for (int p = 0; p < NS; ++p) {
@@ -244,7 +231,7 @@ int b7_i8_panel_slice(b7_ctx* ctx, cudaStream_t st, const double* fac, int Np, i
                       size_t p_stride, double* sig, int s0, int count) {
   const int NB = Np / 128;
   if (row0_blk >= NB) return 0;
-  slice_panel_kernel<<<dim3(NB - row0_blk, count), 128, 0, st>>>(fac, (long long)Np * Np, Np, kb0, (kb1 - kb0) * 2, row0_blk, pA, pB,
+  slice_panel_kernel<<<dim3(NB - row0_blk, count), SLICE_THREADS, 0, st>>>(fac, (long long)Np * Np, Np, kb0, (kb1 - kb0) * 2, row0_blk, pA, pB,
                                                                 (long long)p_stride, sig, s0);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());

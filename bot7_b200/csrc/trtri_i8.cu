@@ -43,34 +43,23 @@ struct Src {            // a block matrix in the tiled fp64 layout, addressed pe
 
 // rows -> A-layout slices  sA[pair * nb + it][ks][p][kc][128][16]  and sig[(pair * nb + it) * 128 + row]
 // k blocks of row block `it`: 0 .. it when the operand is lower triangular, else 0 .. nb-1
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SLICE_THREADS)
 slice_rows_kernel(Src m, int NB, int nb, int tri, int8_t* __restrict__ sA, long long sA_draw, double* __restrict__ sig, long long sig_draw) {
-  const int it = blockIdx.x, pair = blockIdx.y, z = blockIdx.z, row = threadIdx.x;
+  __shared__ double s_red[SLICE_THREADS];
+  const int it = blockIdx.x, pair = blockIdx.y, z = blockIdx.z, row = threadIdx.x & 127, q = threadIdx.x >> 7;
   if (it >= n2_of(NB, nb, pair)) return;
-  const int kw = (tri ? it + 1 : nb) * 128, KS = 2 * nb;
+  const int n_kc = (tri ? it + 1 : nb) * 8, KS = 2 * nb;
   const double* src = m.base + (long long)z * m.draw + tile_off(m.kta, m.rb0 + pair * m.pair_rb + it, (m.cb0 + pair * m.pair_cb) * 8);
   double mx = 0.0;
   bool bad = false;
-  for (int k4 = 0; k4 < kw; k4 += 4) {
-    const double* p = src + elem_off(row, k4);
-    bad |= !(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]));
-    mx = fmax(mx, fmax(fmax(fabs(p[0]), fabs(p[1])), fmax(fabs(p[2]), fabs(p[3]))));
-  }
-  int e = 0;
-  frexp(mx, &e);
-  const double sg = bad ? __longlong_as_double(0x7ff8000000000000LL) : (mx > 0.0 ? ldexp(1.0, e) : 1.0);
-  const double inv = bad ? 0.0 : 1.0 / sg;
-  sig[(long long)z * sig_draw + (pair * nb + it) * TM + row] = sg;
+  for (int kc = q; kc < n_kc; kc += 4) chunk_max(src + elem_off(row, kc * 16), mx, bad);
+  const double sg = row_scale(mx, bad, s_red, row, q);
+  const double inv = sg != sg ? 0.0 : 1.0 / sg;
+  if (q == 0) sig[(long long)z * sig_draw + (pair * nb + it) * TM + row] = sg;
   int8_t* dst = sA + (long long)z * sA_draw + (long long)(pair * nb + it) * KS * A_STAGE;
-  for (int kc = 0; kc < kw / 16; ++kc) {
+  for (int kc = q; kc < n_kc; kc += 4) {
     uint32_t pk[4][NS];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      unsigned long long zz[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) zz[i] = digit_bytes(src[elem_off(row, kc * 16 + g * 4 + i)] * inv);
-      pack4(zz, pk[g]);
-    }
+    chunk_digits(src + elem_off(row, kc * 16), inv, pk);
     const int ks = kc / KC, kcc = kc % KC;
 #pragma unroll
     for (int p = 0; p < NS; ++p)
@@ -81,48 +70,46 @@ slice_rows_kernel(Src m, int NB, int nb, int tri, int8_t* __restrict__ sA, long 
 
 // columns -> B-layout slices  sB[(pair * nb + nt) * 2 + half][ks][p][kc][64][16]  and sig[(pair * nb + nt) * 128 + col]
 // k (row) blocks of column block `nt`: nt .. nb-1 when the operand is lower triangular (X11), else 0 .. n2-1 (L21)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SLICE_THREADS)
 slice_cols_kernel(Src m, int NB, int nb, int tri, int8_t* __restrict__ sB, long long sB_draw, double* __restrict__ sig, long long sig_draw) {
-  const int nt = blockIdx.x, pair = blockIdx.y, z = blockIdx.z, n = threadIdx.x;
+  __shared__ double s_red[SLICE_THREADS];
+  const int nt = blockIdx.x, pair = blockIdx.y, z = blockIdx.z, n = threadIdx.x & 127, q = threadIdx.x >> 7;
   const int n2 = n2_of(NB, nb, pair);
   if (n2 == 0) return;
-  const int kb0 = tri ? nt : 0, kb1 = tri ? nb : n2, KS = 2 * nb;
+  const int kc0 = (tri ? nt : 0) * 8, kc1 = (tri ? nb : n2) * 8, KS = 2 * nb;
   const double* base = m.base + (long long)z * m.draw;
   const int ct = (m.cb0 + pair * m.pair_cb + nt) * 8 + (n >> 4);
   const int coff = ((n & 15) >> 2) * (TM * 4) + (n & 3);            // elem_off(k, n & 15) = coff + 4 k
   double mx = 0.0;
   bool bad = false;
-  for (int kb = kb0; kb < kb1; ++kb) {
-    const double* t = base + tile_off(m.kta, m.rb0 + pair * m.pair_rb + kb, ct) + coff;
-    for (int k = 0; k < 128; ++k) {
+  for (int kc = kc0 + q; kc < kc1; kc += 4) {
+    const double* t = base + tile_off(m.kta, m.rb0 + pair * m.pair_rb + (kc >> 3), ct) + coff + 4 * 16 * (kc & 7);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
       const double x = t[4 * k];
       bad |= !isfinite(x);
       mx = fmax(mx, fabs(x));
     }
   }
-  int e = 0;
-  frexp(mx, &e);
-  const double sg = bad ? __longlong_as_double(0x7ff8000000000000LL) : (mx > 0.0 ? ldexp(1.0, e) : 1.0);
-  const double inv = bad ? 0.0 : 1.0 / sg;
-  sig[(long long)z * sig_draw + (pair * nb + nt) * TM + n] = sg;
+  const double sg = row_scale(mx, bad, s_red, n, q);
+  const double inv = sg != sg ? 0.0 : 1.0 / sg;
+  if (q == 0) sig[(long long)z * sig_draw + (pair * nb + nt) * TM + n] = sg;
   int8_t* dst = sB + (long long)z * sB_draw + (long long)((pair * nb + nt) * 2 + (n >> 6)) * KS * B_STAGE + (n & 63) * 16;
-  for (int kb = kb0; kb < kb1; ++kb) {
-    const double* t = base + tile_off(m.kta, m.rb0 + pair * m.pair_rb + kb, ct) + coff;
-    for (int kc = 0; kc < 8; ++kc) {
-      uint32_t pk[4][NS];
+  for (int kc = kc0 + q; kc < kc1; kc += 4) {
+    const double* t = base + tile_off(m.kta, m.rb0 + pair * m.pair_rb + (kc >> 3), ct) + coff + 4 * 16 * (kc & 7);
+    uint32_t pk[4][NS];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        unsigned long long zz[4];
+    for (int g = 0; g < 4; ++g) {
+      unsigned long long zz[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) zz[i] = digit_bytes(t[4 * (kc * 16 + g * 4 + i)] * inv);
-        pack4(zz, pk[g]);
-      }
-      const int gkc = kb * 8 + kc, ks = gkc / KC, kcc = gkc % KC;
-#pragma unroll
-      for (int p = 0; p < NS; ++p)
-        *reinterpret_cast<uint4*>(dst + (long long)ks * B_STAGE + p * (KC * TN * 16) + kcc * (TN * 16)) =
-            make_uint4(pk[0][p], pk[1][p], pk[2][p], pk[3][p]);
+      for (int i = 0; i < 4; ++i) zz[i] = digit_bytes(t[4 * (g * 4 + i)] * inv);
+      pack4(zz, pk[g]);
     }
+    const int ks = kc / KC, kcc = kc % KC;
+#pragma unroll
+    for (int p = 0; p < NS; ++p)
+      *reinterpret_cast<uint4*>(dst + (long long)ks * B_STAGE + p * (KC * TN * 16) + kcc * (TN * 16)) =
+          make_uint4(pk[0][p], pk[1][p], pk[2][p], pk[3][p]);
   }
 }
 
@@ -320,14 +307,14 @@ static int trtri_i8_group(b7_gp* gp, int s0, int count, size_t rows_max, size_t 
     const Src x11{fac0, fs, Np / 16, 0, 2 * nb, 0, 2 * nb};
     const Src wsrc{W, (long long)w_draw, nb * 8, 0, nb, 0, 0};
     // W = X22 L21
-    slice_rows_kernel<<<grid, 128, 0, st>>>(x22, NB, nb, 1, sA, (long long)sA_draw, sigA, (long long)sig_draw);
-    slice_cols_kernel<<<grid, 128, 0, st>>>(l21, NB, nb, 0, sB, (long long)sB_draw, sigB, (long long)sig_draw);
+    slice_rows_kernel<<<grid, SLICE_THREADS, 0, st>>>(x22, NB, nb, 1, sA, (long long)sA_draw, sigA, (long long)sig_draw);
+    slice_cols_kernel<<<grid, SLICE_THREADS, 0, st>>>(l21, NB, nb, 0, sB, (long long)sB_draw, sigB, (long long)sig_draw);
     b7_count(ctx, 2);
     B7_CHECK(launch_gemm(ctx, sA, (long long)sA_draw, sB, (long long)sB_draw, sigA, sigB, (long long)sig_draw,
                          Out{W, (long long)w_draw, nb * 8, 0, nb, 0, 0}, NB, nb, n_pairs, 0, 1.0, count));
     // X21 = - W X11
-    slice_rows_kernel<<<grid, 128, 0, st>>>(wsrc, NB, nb, 0, sA, (long long)sA_draw, sigA, (long long)sig_draw);
-    slice_cols_kernel<<<grid, 128, 0, st>>>(x11, NB, nb, 1, sB, (long long)sB_draw, sigB, (long long)sig_draw);
+    slice_rows_kernel<<<grid, SLICE_THREADS, 0, st>>>(wsrc, NB, nb, 0, sA, (long long)sA_draw, sigA, (long long)sig_draw);
+    slice_cols_kernel<<<grid, SLICE_THREADS, 0, st>>>(x11, NB, nb, 1, sB, (long long)sB_draw, sigB, (long long)sig_draw);
     b7_count(ctx, 2);
     B7_CHECK(launch_gemm(ctx, sA, (long long)sA_draw, sB, (long long)sB_draw, sigA, sigB, (long long)sig_draw,
                          Out{fac0, fs, Np / 16, nb, 2 * nb, 0, 2 * nb}, NB, nb, n_pairs, 1, -1.0, count));
