@@ -198,6 +198,7 @@ void b7_shutdown(b7_ctx* ctx) {
   dev_free(ctx, ctx->ks);
   dev_free(ctx, ctx->moments);
   dev_free(ctx, ctx->xs_stage);
+  dev_free(ctx, ctx->i8_partial);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->stream2);
   { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
@@ -659,11 +660,12 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
       B7_CHECK(b7_i8_cov_slices(ctx, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau, ksS));
       t.stop(1);
     }
+    B7_CHECK(grow(ctx, &ctx->i8_partial, &ctx->i8_partial_bytes, b7_i8_partial_bytes(gp->Np, rp64)));
     StageTimer t(ctx, ST_POSTERIOR);
     B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * B7_I8_SLICES, gp->sigma + (size_t)s * gp->Np,
                                     gp->beta + (size_t)s * gp->Np, gp->Np, ksS, A, rows, gp->d, gp->Xt, gp->par + (size_t)s * kParStride,
-                                    gp->kernel, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], mean, var));
-    t.stop(1);
+                                    gp->kernel, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], ctx->i8_partial, mean, var));
+    t.stop(1);   // one posterior pass (the few-microsecond finish kernel rides along)
     return 0;
   }
   {

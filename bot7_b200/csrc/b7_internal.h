@@ -51,6 +51,8 @@ struct b7_ctx {
   size_t moments_bytes = 0;
   double* xs_stage = nullptr;  // device staging of host candidate points
   size_t xs_bytes = 0;
+  double* i8_partial = nullptr;   // [candidate tile][row block][64][2] partial sums of the INT8 posterior pass
+  size_t i8_partial_bytes = 0;
 };
 
 struct b7_grid {
@@ -151,7 +153,8 @@ int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int
                      const double* par, double tau, int8_t* ksS);
 int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
                            const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
-                           int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var);
+                           int64_t cols_pad, double tau, double sf2, double mconst, double* partial, double* mean, double* var);
+size_t b7_i8_partial_bytes(int Np, int64_t cols_pad);   // scratch of the launch above: per-row-block partial sums
 // score.cu
 int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,
                     double tradeoff, int bound, double sign, double fmin, const int64_t* removed, int64_t n_removed,

@@ -20,6 +20,7 @@
 // slice-of-L^-1-major so that the 4 KB A operand stays in the tensor core's collector while it meets its
 // 8 - p partner slices of K* (tcgen05.mma ... collector::a::fill / use / lastuse).
 #include <math.h>
+#include <stdlib.h>
 
 #include "b7_internal.h"
 #include "exp_neg.cuh"
@@ -149,8 +150,8 @@ __device__ __forceinline__ double lane_transpose_sum(double (&x)[32], int lane) 
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
 posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, const double* __restrict__ beta,
-                    int Np, int NB, const int8_t* __restrict__ ksS, const double* __restrict__ cand, long long rows, int d,
-                    const double* __restrict__ Xt, const double* __restrict__ par, int kernel, double tau, double sf2, double mconst, double* __restrict__ mean, double* __restrict__ var) {
+                    int Np, int NB, const int8_t* __restrict__ ksS, double tau, int chunk, int group, int n_tiles,
+                    double* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem[];
   double* red = reinterpret_cast<double*>(smem + NSTAGE * STAGE);             // [2 parity][4 warps][64 cols][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE + RED_BYTES);
@@ -158,6 +159,16 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KS_ALL = Np / KB;
+  // A CTA owns `chunk` consecutive row blocks of one 64-candidate tile and leaves one partial (sum v^2, sum v beta)
+  // per candidate and row block; posterior_i8_finish_kernel adds them in row-block order.  CTAs are issued in
+  // groups of `group` tiles, inside a group heaviest row blocks first: only one or two groups are in flight, so
+  // their K* slices (1.8 MB per tile at N = 4096, re-read once per row block) stay in L2 next to the L^-1
+  // slices, and the launch ends on the lightest pieces.
+  const int cpt = (NB + chunk - 1) / chunk;                      // CTAs per tile
+  const int g = blockIdx.x / (group * cpt), within = blockIdx.x % (group * cpt);
+  const int g_tiles = n_tiles - g * group < group ? n_tiles - g * group : group;
+  const int tile = g * group + within % g_tiles, cidx = cpt - 1 - within / g_tiles;
+  const int rb0 = cidx * chunk, rb1 = rb0 + chunk < NB ? rb0 + chunk : NB;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
@@ -177,11 +188,11 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
     // ---- producer: stream (rb, ks) stages.  The whole warp walks the loop and one elected lane issues the
     // copies: under `if (lane == 0)` the compiler wraps every uniform-datapath instruction (UBLKCP, UTCIMMA) in
     // an ELECT / BRA.U.ANY serialisation loop, which made the MMA issue the bottleneck (61 clk per MMA). ----
-    const int8_t* gB = ksS + (long long)blockIdx.x * KS_ALL * B_STAGE;
+    const int8_t* gB = ksS + (long long)tile * KS_ALL * B_STAGE;
     int slot = 0;
     unsigned phase = 1;                    // parity of the *previous* use of the slot; first round needs no wait
     bool wrapped = false;
-    for (int rb = 0; rb < NB; ++rb)
+    for (int rb = rb0; rb < rb1; ++rb)
       for (int ks = 0; ks < (TM / KB) * (rb + 1); ++ks) {
         if (wrapped) mbar_wait(empty + slot, phase);
         if (elect_one()) {
@@ -199,8 +210,8 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     int slot = 0;
     unsigned phase = 0;
-    for (int rb = 0; rb < NB; ++rb) {
-      if (rb > 0) { mbar_wait(acc_empty, (unsigned)((rb - 1) & 1)); tc_fence_after(); }
+    for (int rb = rb0; rb < rb1; ++rb) {
+      if (rb > rb0) { mbar_wait(acc_empty, (unsigned)((rb - rb0 - 1) & 1)); tc_fence_after(); }
       const int n_ks = (TM / KB) * (rb + 1);
       for (int ks = 0; ks < n_ks; ++ks) {
         mbar_wait(full + slot, phase);
@@ -238,9 +249,8 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
     }
   } else {
     // ---- epilogue warps 0-3: thread = L^-1 row (TMEM lane), 64 candidate columns ----
-    double run2 = 0.0, run1 = 0.0;         // meaningful in threads 0..63 (candidate c = tid)
-    for (int rb = 0; rb < NB; ++rb) {
-      mbar_wait(acc_full, (unsigned)(rb & 1));
+    for (int rb = rb0; rb < rb1; ++rb) {
+      mbar_wait(acc_full, (unsigned)((rb - rb0) & 1));
       tc_fence_after();
       double v[TN];
 #pragma unroll
@@ -261,7 +271,7 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
       if (lane == 0) mbar_arrive(acc_empty);     // TMEM drained: the next row block may start
       const int row = rb * TM + tid;
       const double sc = sigma[row] * tau, b = beta[row];
-      double* rr = red + (rb & 1) * (4 * TN * 2);
+      double* rr = red + ((rb - rb0) & 1) * (4 * TN * 2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         double x[32];
@@ -276,31 +286,45 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
       }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       if (tid < TN) {
-        run2 += ((rr[(0 * TN + tid) * 2] + rr[(1 * TN + tid) * 2]) + rr[(2 * TN + tid) * 2]) + rr[(3 * TN + tid) * 2];
-        run1 += ((rr[(0 * TN + tid) * 2 + 1] + rr[(1 * TN + tid) * 2 + 1]) + rr[(2 * TN + tid) * 2 + 1]) + rr[(3 * TN + tid) * 2 + 1];
+        double* out = partial + (((long long)tile * NB + rb) * TN + tid) * 2;
+        out[0] = ((rr[(0 * TN + tid) * 2] + rr[(1 * TN + tid) * 2]) + rr[(2 * TN + tid) * 2]) + rr[(3 * TN + tid) * 2];
+        out[1] = ((rr[(0 * TN + tid) * 2 + 1] + rr[(1 * TN + tid) * 2 + 1]) + rr[(2 * TN + tid) * 2 + 1]) + rr[(3 * TN + tid) * 2 + 1];
       }
-    }
-    if (tid < TN) {
-      const long long c = (long long)blockIdx.x * TN + tid;
-      // integers cannot carry a NaN: where the K* row of the fp64 path would be NaN (a NaN coordinate, or an infinite
-      // one under Matern: inf * 0), poison the results here.  With finite observations the scaled distance to
-      // the first one decides it for the whole row.
-      double r2 = 0.0;
-      if (c < rows)
-        for (int j = 0; j < d; ++j) {
-          const double t = (cand[c * d + j] - Xt[(long long)j * Np]) * par[j];
-          r2 = fma(t, t, r2);
-        }
-      const bool nan_row = (r2 != r2) || (kernel == B7_KERNEL_MATERN52 && isinf(r2));
-      const double poison = nan_row ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
-      const double vv = sf2 - run2;
-      var[c] = (vv > 0.0 ? vv : (vv != vv ? vv : 0.0)) + poison;
-      mean[c] = mconst + run1 + poison;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// var = sf2 - sum_rb sum v^2, mean = m + sum_rb sum v beta, row blocks added in ascending order (fixed order:
+// deterministic and independent of how the row blocks were split over CTAs)
+__global__ void __launch_bounds__(128)
+posterior_i8_finish_kernel(const double* __restrict__ partial, int NB, int Np, const double* __restrict__ cand, long long rows, int d,
+                           const double* __restrict__ Xt, const double* __restrict__ par, int kernel, double sf2, double mconst,
+                           long long cols_pad, double* __restrict__ mean, double* __restrict__ var) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols_pad) return;
+  const double* p = partial + ((c / TN) * NB * TN + c % TN) * 2;
+  double run2 = 0.0, run1 = 0.0;
+  for (int rb = 0; rb < NB; ++rb) {
+    run2 += p[(long long)rb * TN * 2];
+    run1 += p[(long long)rb * TN * 2 + 1];
+  }
+  // integers cannot carry a NaN: where the K* row of the fp64 path would be NaN (a NaN coordinate, or an infinite
+  // one under Matern: inf * 0), poison the results here.  With finite observations the scaled distance to
+  // the first one decides it for the whole row.
+  double r2 = 0.0;
+  if (c < rows)
+    for (int j = 0; j < d; ++j) {
+      const double t = (cand[c * d + j] - Xt[(long long)j * Np]) * par[j];
+      r2 = fma(t, t, r2);
+    }
+  const bool nan_row = (r2 != r2) || (kernel == B7_KERNEL_MATERN52 && isinf(r2));
+  const double poison = nan_row ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+  const double vv = sf2 - run2;
+  var[c] = (vv > 0.0 ? vv : (vv != vv ? vv : 0.0)) + poison;
+  mean[c] = mconst + run1 + poison;
 }
 
 bool g_attr_i8[16] = {false};
@@ -338,17 +362,28 @@ int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int
   return launch_cov_slices<40>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
 }
 
+size_t b7_i8_partial_bytes(int Np, int64_t cols_pad) { return (size_t)(cols_pad / TN) * (Np / TM) * TN * 2 * sizeof(double); }
+
 int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
                            const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
-                           int64_t cols_pad, double tau, double sf2, double mconst, double* mean, double* var) {
+                           int64_t cols_pad, double tau, double sf2, double mconst, double* partial, double* mean, double* var) {
   if (!g_attr_i8[ctx->device & 15]) {
     B7_CUDA(cudaFuncSetAttribute(posterior_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     g_attr_i8[ctx->device & 15] = true;
   }
   if (cols_pad <= 0) return 0;
-  posterior_i8_kernel<<<(unsigned)(cols_pad / TN), I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, Np / TM, ksS, cand, rows, d, Xt, par, kernel, tau,
-                                                                                      sf2, mconst, mean, var);
-  b7_count(ctx);
+  const int NB = Np / TM;
+  static const int chunk_env = getenv("B7_POST_CHUNK") ? atoi(getenv("B7_POST_CHUNK")) : 0;
+  // measured at N = 4096 (64 launches, ms): whole tile per CTA 203.6, chunk 4 198.1, chunk 2 194.0 (+-2)
+  const int chunk = chunk_env > 0 ? (chunk_env < NB ? chunk_env : NB) : (NB < 2 ? NB : 2);
+  const int cpt = (NB + chunk - 1) / chunk;
+  static const int group_env = getenv("B7_POST_GROUP") ? atoi(getenv("B7_POST_GROUP")) : 0;
+  const int n_tiles = (int)(cols_pad / TN), group = group_env > 0 ? group_env : 16;
+  posterior_i8_kernel<<<(unsigned)n_tiles * cpt, I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, NB, ksS, tau, chunk, group, n_tiles,
+                                                                                    partial);
+  posterior_i8_finish_kernel<<<(unsigned)((cols_pad + 127) / 128), 128, 0, ctx->stream>>>(partial, NB, Np, cand, rows, d, Xt, par, kernel, sf2,
+                                                                                         mconst, cols_pad, mean, var);
+  b7_count(ctx, 2);
   B7_CUDA(cudaGetLastError());
   return 0;
 }

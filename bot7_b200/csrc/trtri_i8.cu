@@ -246,7 +246,7 @@ int launch_gemm(b7_ctx* ctx, const int8_t* sA, long long sA_draw, const int8_t* 
                 const double* sigB, long long sig_draw, Out o, int NB, int nb, int n_pairs, int mode, double sign, int count) {
   const long long n_items = (long long)count * n_pairs * nb * nb * 2;
   static const int chunk_env = getenv("B7_TRTRI_CHUNK") ? atoi(getenv("B7_TRTRI_CHUNK")) : 0;
-  const int chunk = chunk_env > 0 ? chunk_env : 8;
+  const int chunk = chunk_env > 0 ? chunk_env : 4;   // fewer draws in flight: their slices stay in L2 (12.9 vs 13.5 ms at chunk 8)
   const int grid = (int)((n_items + chunk - 1) / chunk);
   gemm_i8_kernel<<<grid, THREADS, SMEM, ctx->stream>>>(sA, sA_draw, sB, sB_draw, sigA, sigB, sig_draw, o, NB, nb, n_pairs, mode, sign, n_items,
                                                        chunk);
