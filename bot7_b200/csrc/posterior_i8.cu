@@ -46,6 +46,8 @@ constexpr int B_STAGE = NS * TN * KB;      // 28672 B
 constexpr int STAGE = A_STAGE + B_STAGE;   // 86016 B
 constexpr int NSTAGE = I8_NSTAGE;
 static_assert(STAGE % 1024 == 0 && KB % 32 == 0 && 64 % KB == 0, "stage geometry");
+static_assert(KB == b7i8::gemm::KB && TM == b7i8::gemm::TM && TN == b7i8::gemm::TN && NSTAGE == b7i8::gemm::NSTAGE,
+              "posterior_i8_kernel issues its MMAs through the shared stage of i8_common.cuh");
 constexpr int I8_THREADS = 192;
 constexpr int RED_BYTES = 2 * 4 * TN * 2 * 8;           // [rb parity][warp][candidate][sum v^2, sum v beta]
 constexpr int I8_SMEM = NSTAGE * STAGE + RED_BYTES + 1024;   // stages + reduction scratch + barriers
@@ -146,6 +148,34 @@ __device__ __forceinline__ double lane_transpose_sum(double (&x)[32], int lane) 
   return x[0];
 }
 
+// Enumeration of the work items of posterior_i8_kernel (same on every warp role).  Tiles are taken in groups of
+// `group`; inside a group the order is pair level, then tile.  Pair level l = row-block chunks l and cpt-1-l.
+struct Walk {
+  int NB, chunk, group, n_tiles;
+  __device__ __forceinline__ int cpt() const { return (NB + chunk - 1) / chunk; }          // chunks per tile
+  __device__ __forceinline__ int npl() const { return (cpt() + 1) / 2; }                   // pair levels per tile
+  __device__ __forceinline__ int n_items() const { return n_tiles * npl(); }
+  __device__ __forceinline__ int grp(int item) const {
+    const int g = item / (group * npl()), last = (n_tiles - 1) / group;
+    return g < last ? g : last;
+  }
+  __device__ __forceinline__ int g_tiles(int g) const { return n_tiles - g * group < group ? n_tiles - g * group : group; }
+  __device__ __forceinline__ int tile(int item) const {
+    const int g = grp(item);
+    return g * group + (item - g * group * npl()) % g_tiles(g);
+  }
+  __device__ __forceinline__ int level(int item) const {
+    const int g = grp(item);
+    return (item - g * group * npl()) / g_tiles(g);
+  }
+  __device__ __forceinline__ int parts(int item) const { return 2 * level(item) == cpt() - 1 ? 1 : 2; }
+  __device__ __forceinline__ int rb_begin(int item, int part) const { return (part == 0 ? level(item) : cpt() - 1 - level(item)) * chunk; }
+  __device__ __forceinline__ int rb_end(int item, int part) const {
+    const int e = rb_begin(item, part) + chunk;
+    return e < NB ? e : NB;
+  }
+};
+
 // ---- the kernel ----------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
@@ -159,16 +189,13 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KS_ALL = Np / KB;
-  // A CTA owns `chunk` consecutive row blocks of one 64-candidate tile and leaves one partial (sum v^2, sum v beta)
-  // per candidate and row block; posterior_i8_finish_kernel adds them in row-block order.  CTAs are issued in
-  // groups of `group` tiles, inside a group heaviest row blocks first: only one or two groups are in flight, so
-  // their K* slices (1.8 MB per tile at N = 4096, re-read once per row block) stay in L2 next to the L^-1
-  // slices, and the launch ends on the lightest pieces.
-  const int cpt = (NB + chunk - 1) / chunk;                      // CTAs per tile
-  const int g = blockIdx.x / (group * cpt), within = blockIdx.x % (group * cpt);
-  const int g_tiles = n_tiles - g * group < group ? n_tiles - g * group : group;
-  const int tile = g * group + within % g_tiles, cidx = cpt - 1 - within / g_tiles;
-  const int rb0 = cidx * chunk, rb1 = rb0 + chunk < NB ? rb0 + chunk : NB;
+  // Work items of equal weight: a 64-candidate tile x a pair of row-block chunks (chunk l and chunk cpt-1-l: the
+  // triangular L^-1 makes their stage counts add up to the same number for every l).  Each item leaves one partial
+  // (sum v^2, sum v beta) per candidate and row block; posterior_i8_finish_kernel adds them in row-block order.
+  // Items are ordered in groups of `group` tiles and dealt round-robin to a persistent grid (one CTA per SM, the
+  // TMA / MMA / epilogue pipeline never drains between items): only one or two groups are in flight, so their K*
+  // slices (1.8 MB per tile at N = 4096, re-read once per row block) stay in L2 next to the L^-1 slices.
+  const Walk wk{NB, chunk, group, n_tiles};
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
@@ -188,69 +215,59 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
     // ---- producer: stream (rb, ks) stages.  The whole warp walks the loop and one elected lane issues the
     // copies: under `if (lane == 0)` the compiler wraps every uniform-datapath instruction (UBLKCP, UTCIMMA) in
     // an ELECT / BRA.U.ANY serialisation loop, which made the MMA issue the bottleneck (61 clk per MMA). ----
-    const int8_t* gB = ksS + (long long)tile * KS_ALL * B_STAGE;
     int slot = 0;
     unsigned phase = 1;                    // parity of the *previous* use of the slot; first round needs no wait
     bool wrapped = false;
-    for (int rb = rb0; rb < rb1; ++rb)
-      for (int ks = 0; ks < (TM / KB) * (rb + 1); ++ks) {
-        if (wrapped) mbar_wait(empty + slot, phase);
-        if (elect_one()) {
-          uint8_t* st = smem + slot * STAGE;
-          mbar_arrive_expect_tx(full + slot, STAGE);
-          bulk_g2s(st, facS + ((long long)rb * KS_ALL + ks) * A_STAGE, A_STAGE, full + slot);
-          bulk_g2s(st + A_STAGE, gB + (long long)ks * B_STAGE, B_STAGE, full + slot);
-        }
-        __syncwarp();
-        if (++slot == NSTAGE) { slot = 0; phase ^= 1u; wrapped = true; }
-      }
+    for (int item = blockIdx.x; item < wk.n_items(); item += gridDim.x) {
+      const int tile = wk.tile(item);
+      const int8_t* gB = ksS + (long long)tile * KS_ALL * B_STAGE;
+      for (int part = 0; part < wk.parts(item); ++part)
+        for (int rb = wk.rb_begin(item, part); rb < wk.rb_end(item, part); ++rb)
+          for (int ks = 0; ks < (TM / KB) * (rb + 1); ++ks) {
+            if (wrapped) mbar_wait(empty + slot, phase);
+            if (elect_one()) {
+              uint8_t* st = smem + slot * STAGE;
+              mbar_arrive_expect_tx(full + slot, STAGE);
+              bulk_g2s(st, facS + ((long long)rb * KS_ALL + ks) * A_STAGE, A_STAGE, full + slot);
+              bulk_g2s(st + A_STAGE, gB + (long long)ks * B_STAGE, B_STAGE, full + slot);
+            }
+            __syncwarp();
+            if (++slot == NSTAGE) { slot = 0; phase ^= 1u; wrapped = true; }
+          }
+    }
   } else if (warp == 5) {
     // ---- MMA issuer (warp-converged, one elected lane) ----
     // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N = 64, M = 128
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    int slot = 0;
+    int slot = 0, done = 0;
     unsigned phase = 0;
-    for (int rb = rb0; rb < rb1; ++rb) {
-      if (rb > rb0) { mbar_wait(acc_empty, (unsigned)((rb - rb0 - 1) & 1)); tc_fence_after(); }
-      const int n_ks = (TM / KB) * (rb + 1);
-      for (int ks = 0; ks < n_ks; ++ks) {
-        mbar_wait(full + slot, phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint8_t* sa = smem + slot * STAGE;
-          // descriptors of slice 1 / first k half; the others differ only in the 16-byte-unit address field
-          const uint64_t da0 = umma_desc(sa, TM * 16, 128), db0 = umma_desc(sa + A_STAGE, TN * 16, 128);
-#pragma unroll
-          for (int k2 = 0; k2 < KB / 32; ++k2) {
-            // slice p of L^-1 meets slices 1 .. NS + 1 - p of K*; class p + q accumulates in its own 64 columns,
-            // and every class sees its first product in the p = 1 group
-#pragma unroll
-            for (int p = 1; p <= NS; ++p) {
-              const uint64_t da = da0 + (uint64_t)(((p - 1) * (KC * TM * 16) + k2 * (2 * TM * 16)) >> 4);
-              const uint32_t acc = (ks == 0 && k2 == 0 && p == 1) ? 0u : 1u;
-              const int nq = NS + 1 - p;
-#pragma unroll
-              for (int q = 1; q <= nq; ++q) {
-                const uint64_t db = db0 + (uint64_t)(((q - 1) * (KC * TN * 16) + k2 * (2 * TN * 16)) >> 4);
-                const uint32_t dcol = tmem + (uint32_t)((p + q - 2) * TN);
-                if (nq == 1) umma_i8<0>(dcol, da, db, idesc, acc);
-                else if (q == 1) umma_i8<1>(dcol, da, db, idesc, acc);
-                else if (q == nq) umma_i8<3>(dcol, da, db, idesc, acc);
-                else umma_i8<2>(dcol, da, db, idesc, acc);
-              }
+    for (int item = blockIdx.x; item < wk.n_items(); item += gridDim.x)
+      for (int part = 0; part < wk.parts(item); ++part)
+        for (int rb = wk.rb_begin(item, part); rb < wk.rb_end(item, part); ++rb, ++done) {
+          if (done > 0) { mbar_wait(acc_empty, (unsigned)((done - 1) & 1)); tc_fence_after(); }
+          const int n_ks = (TM / KB) * (rb + 1);
+          for (int ks = 0; ks < n_ks; ++ks) {
+            mbar_wait(full + slot, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              // slice p of L^-1 meets slices 1 .. 8 - p of K* from the collector; class p + q accumulates in its own
+              // 64 TMEM columns, and every class sees its first product in the p = 1 group (i8_common.cuh)
+              b7i8::gemm::mma_stage(smem + slot * STAGE, tmem, idesc, ks == 0);
+              umma_commit(empty + slot);                   // frees the stage once these MMAs have read it
+              if (ks == n_ks - 1) umma_commit(acc_full);   // all MMAs of the row block done -> epilogue may read TMEM
             }
+            __syncwarp();
+            if (++slot == NSTAGE) { slot = 0; phase ^= 1u; }
           }
-          umma_commit(empty + slot);                   // frees the stage once these MMAs have read it
-          if (ks == n_ks - 1) umma_commit(acc_full);   // all MMAs of the row block done -> epilogue may read TMEM
         }
-        __syncwarp();
-        if (++slot == NSTAGE) { slot = 0; phase ^= 1u; }
-      }
-    }
   } else {
     // ---- epilogue warps 0-3: thread = L^-1 row (TMEM lane), 64 candidate columns ----
-    for (int rb = rb0; rb < rb1; ++rb) {
-      mbar_wait(acc_full, (unsigned)((rb - rb0) & 1));
+    int done = 0;
+    for (int item = blockIdx.x; item < wk.n_items(); item += gridDim.x) {
+    const int tile = wk.tile(item);
+    for (int part = 0; part < wk.parts(item); ++part)
+    for (int rb = wk.rb_begin(item, part); rb < wk.rb_end(item, part); ++rb, ++done) {
+      mbar_wait(acc_full, (unsigned)(done & 1));
       tc_fence_after();
       double v[TN];
 #pragma unroll
@@ -271,7 +288,7 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
       if (lane == 0) mbar_arrive(acc_empty);     // TMEM drained: the next row block may start
       const int row = rb * TM + tid;
       const double sc = sigma[row] * tau, b = beta[row];
-      double* rr = red + ((rb - rb0) & 1) * (4 * TN * 2);
+      double* rr = red + (done & 1) * (4 * TN * 2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         double x[32];
@@ -290,6 +307,7 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
         out[0] = ((rr[(0 * TN + tid) * 2] + rr[(1 * TN + tid) * 2]) + rr[(2 * TN + tid) * 2]) + rr[(3 * TN + tid) * 2];
         out[1] = ((rr[(0 * TN + tid) * 2 + 1] + rr[(1 * TN + tid) * 2 + 1]) + rr[(2 * TN + tid) * 2 + 1]) + rr[(3 * TN + tid) * 2 + 1];
       }
+    }
     }
   }
   tc_fence_before();
@@ -374,13 +392,15 @@ int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma,
   if (cols_pad <= 0) return 0;
   const int NB = Np / TM;
   static const int chunk_env = getenv("B7_POST_CHUNK") ? atoi(getenv("B7_POST_CHUNK")) : 0;
-  // measured at N = 4096 (64 launches, ms): whole tile per CTA 203.6, chunk 4 198.1, chunk 2 194.0 (+-2)
+  // measured at N = 4096 (64 launches, ms): whole tile per CTA 204-206; persistent grid over equal-weight items
+  // with chunk 1 / 2 / 4 and groups of 8 / 16 / 32 tiles: 187-194 (differences inside the run-to-run noise)
   const int chunk = chunk_env > 0 ? (chunk_env < NB ? chunk_env : NB) : (NB < 2 ? NB : 2);
   const int cpt = (NB + chunk - 1) / chunk;
   static const int group_env = getenv("B7_POST_GROUP") ? atoi(getenv("B7_POST_GROUP")) : 0;
   const int n_tiles = (int)(cols_pad / TN), group = group_env > 0 ? group_env : 16;
-  posterior_i8_kernel<<<(unsigned)n_tiles * cpt, I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, NB, ksS, tau, chunk, group, n_tiles,
-                                                                                    partial);
+  const int n_items = n_tiles * ((cpt + 1) / 2);
+  posterior_i8_kernel<<<n_items < ctx->sm_count ? n_items : ctx->sm_count, I8_THREADS, I8_SMEM, ctx->stream>>>(facS, sigma, beta, Np, NB, ksS, tau,
+                                                                                                              chunk, group, n_tiles, partial);
   posterior_i8_finish_kernel<<<(unsigned)((cols_pad + 127) / 128), 128, 0, ctx->stream>>>(partial, NB, Np, cand, rows, d, Xt, par, kernel, sf2,
                                                                                          mconst, cols_pad, mean, var);
   b7_count(ctx, 2);
