@@ -40,7 +40,7 @@ struct b7_ctx {
   double stage_ms[ST_COUNT] = {0};
   int64_t stage_calls[ST_COUNT] = {0};
   bool profiling = false;
-  bool use_i8 = false;           // B7_POSTERIOR_I8=1: posterior pass on the INT8 tensor pipe (posterior_i8.cu)
+  bool use_i8 = false;           // posterior pass on the INT8 tensor pipe (posterior_i8.cu); default on, B7_POSTERIOR_I8=0 turns it off
   bool potrf_i8 = true;          // with use_i8: also the k = 512 trailing updates of the Cholesky (B7_POTRF_I8=0: FP64 DMMA)
   bool trtri_i8 = true;          // with use_i8: also the inversion of the factors (B7_TRTRI_I8=0: FP64 DMMA sweep)
   int64_t launches = 0;

@@ -1,8 +1,9 @@
-// Posterior over a candidate panel on the INT8 tensor pipe (opt-in: B7_POSTERIOR_I8=1).
+// Posterior over a candidate panel on the INT8 tensor pipe (the default path; B7_POSTERIOR_I8=0 or
+// b7_set_posterior_path(B7_PATH_FP64_DMMA) select posterior.cu).
 //
 // Same mathematics as posterior.cu (V = L^-1 K*^T, var = sf2 - colsumsq(V), mean = m + V^T beta) and the
 // same fp64-level accuracy, but the N^2 product per candidate runs on tcgen05.mma.kind::i8 (measured
-// 3.9 POPS on B200, tools/i8_mma_probe.cu, against 37 TFLOP/s for the FP64 DMMA pipe) through an
+// 4.2 POPS on B200, tools/i8_mma_probe.cu, against 37 TFLOP/s for the FP64 DMMA pipe) through an
 // error-free slicing of both operands (the "Ozaki scheme"):
 //     a_ik = sigma_i * sum_{p=1..7} d_p(i,k) 2^-(8p-2),   d_p integers in [-128, 127]  (54 bits + sign per entry)
 //     b_ck = tau     * sum_{q=1..7} e_q(c,k) 2^-(8q-2)
@@ -10,15 +11,17 @@
 // Every inner sum is an exact int32 dot product (|d e| <= 2^14, a class holds at most 7 products, so
 // k <= 16384 terms fit), the 28 slice pairs with p + q <= 8 are kept (the dropped ones are below 2^-54 of
 // sigma_i tau per term), and the 7 weight classes are accumulated in 7 x 64 = 448 TMEM columns and combined
-// in fp64 in the epilogue.  Measured against the fp64 path: variance within 1e-13 sf2, mean within 1e-12
-// (see tests).
+// in fp64 in the epilogue.  Measured against the fp64 path: variance within 5e-14 sf2, mean within 5e-11 at
+// N = 4096 (profiles/i8_accuracy_r01.json; tests assert 1e-12 sf2 / 1e-10).
 //
-// One CTA owns 64 candidates and walks the row blocks of L^-1 (128 rows = TMEM lanes).  Warp roles:
-// warp 4 lane 0 streams the slices (already in the UMMA canonical K-major layout in HBM, so a stage is two
-// bulk copies), warp 5 lane 0 issues the MMAs of a stage, warps 0-3 drain the accumulators once per row
-// block (tcgen05.ld), rebuild v in fp64 and reduce v^2 and v*beta over the 128 rows.  The MMAs are issued
-// slice-of-L^-1-major so that the 4 KB A operand stays in the tensor core's collector while it meets its
-// 8 - p partner slices of K* (tcgen05.mma ... collector::a::fill / use / lastuse).
+// A work item is a tile of 64 candidates x a few row blocks of L^-1 (128 rows = TMEM lanes); a persistent grid
+// (one CTA per SM) walks the items.  Warp roles: warp 4 streams the slices (already in the UMMA canonical K-major
+// layout in HBM, so a stage is two bulk copies), warp 5 issues the MMAs of a stage (both from one elect.sync lane
+// of the converged warp), warps 0-3 drain the accumulators once per row block (tcgen05.ld), rebuild v in fp64,
+// reduce v^2 and v*beta over the 128 rows and leave one partial per candidate and row block;
+// posterior_i8_finish_kernel adds the partials in row-block order.  The MMAs are issued slice-of-L^-1-major so
+// that the 4 KB A operand stays in the tensor core's collector while it meets its 8 - p partner slices of K*
+// (tcgen05.mma ... collector::a::fill / use / lastuse).
 #include <math.h>
 #include <stdlib.h>
 
@@ -33,18 +36,12 @@ using namespace b7i8;
 
 namespace {
 
-#ifndef I8_KB
-#define I8_KB 64
-#endif
-#ifndef I8_NSTAGE
-#define I8_NSTAGE 2
-#endif
-constexpr int TM = 128, TN = 64, KB = I8_KB;  // L^-1 rows per block, candidates per CTA, k bytes per stage
+constexpr int TM = 128, TN = 64, KB = 64;  // L^-1 rows per block, candidates per tile, k bytes per stage
 constexpr int KC = KB / 16;                // 16-byte k chunks per stage
 constexpr int A_STAGE = NS * TM * KB;      // 57344 B
 constexpr int B_STAGE = NS * TN * KB;      // 28672 B
 constexpr int STAGE = A_STAGE + B_STAGE;   // 86016 B
-constexpr int NSTAGE = I8_NSTAGE;
+constexpr int NSTAGE = 2;                  // (32-byte stages x 5 were measured slower: 95.6 vs 100 TFLOP/s equivalent)
 static_assert(STAGE % 1024 == 0 && KB % 32 == 0 && 64 % KB == 0, "stage geometry");
 static_assert(KB == b7i8::gemm::KB && TM == b7i8::gemm::TM && TN == b7i8::gemm::TN && NSTAGE == b7i8::gemm::NSTAGE,
               "posterior_i8_kernel issues its MMAs through the shared stage of i8_common.cuh");

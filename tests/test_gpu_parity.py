@@ -328,10 +328,10 @@ def test_nonfinite_candidate_poisons_only_its_own_row(ctx, oracle):
 
 
 def test_int8_trailing_update_of_the_cholesky_matches_the_fp64_one(ctx, oracle):
-    # potrf_i8.cu: with the INT8 path selected, batched fits (>= 4 draws, more than one outer panel) run the k = 512
+    # potrf_i8.cu: with the INT8 path selected, batched fits (S >= 4 draws and S * NB^2 >= 4096) run the k = 512
     # trailing updates as exact int8 slice products; the factor must agree with the all-FP64 factorisation to
-    # rounding level, and both with the oracle
-    Xo, y, hyp, _ = make_problem(oracle, 1500, 6, 5, 10, 1e-3)
+    # rounding level, and both with the oracle.  18 row blocks x 13 draws = 4212.
+    Xo, y, hyp, _ = make_problem(oracle, 2304, 6, 13, 10, 1e-3)
     keep = ctx.posterior_path()
     out = {}
     try:
@@ -339,13 +339,13 @@ def test_int8_trailing_update_of_the_cholesky_matches_the_fp64_one(ctx, oracle):
             ctx.set_posterior_path(path)
             f = models.GPFactors(Xo, y, hyp, flags=L.FIT_LOGML_ONLY)
             assert (np.asarray(f.info) == 0).all()
-            out[path] = (np.array(f.logml), [f.read_factor(s) for s in (0, 4)])
+            out[path] = (np.array(f.logml), [f.read_factor(s) for s in (0, 12)])
             f.free()
     finally:
         ctx.set_posterior_path(keep)
     a, b = out[L.PATH_FP64_DMMA], out[L.PATH_INT8_OZAKI]
     assert rel(a[0], b[0], 1e-300) <= 1e-12
-    for La, Lb, s in zip(a[1], b[1], (0, 4)):
+    for La, Lb, s in zip(a[1], b[1], (0, 12)):
         assert np.max(np.abs(La - Lb)) <= 1e-12 * np.max(np.abs(La))
         assert not np.array_equal(La, Lb)                                # the two arithmetic paths really differ
         ref = oracle.gp_fit(Xo, y, hyp[s], 0)
