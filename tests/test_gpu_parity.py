@@ -378,6 +378,64 @@ def test_block_recursive_int8_inverse_matches_the_fp64_sweep(ctx, oracle, N, S):
         assert np.max(np.abs(b - np.tril(ref))) <= 1e-9 * scale
 
 
+def test_more_than_16384_observations_stay_on_the_fp64_kernels(ctx, oracle):
+    # the int8 slice sums are exact in int32 up to Np = 16384 (7 products x 2^14 x Np < 2^31); beyond that the fit,
+    # the inversion and the posterior must run on the FP64 DMMA kernels even with the INT8 path selected.
+    # Size-independent checks: interpolation of the observations to noise level, 0 <= var <= prior, finite logml.
+    N, d = 16500, 2
+    r = np.random.default_rng(2)
+    X = oracle.sobol_points(d, N)
+    y = oracle.braninhoo(X)
+    y = (y - y.mean()) / y.std()
+    hyp = np.array([[np.log(0.3), np.log(0.3), 0.0, 0.5 * np.log(1e-2), 0.0]])
+    assert ctx.posterior_path() == L.PATH_INT8_OZAKI
+    f = models.GPFactors(X, y, hyp)
+    assert f.info[0] == 0 and np.isfinite(f.logml[0]) and f.padded_n() == 16512
+    idx = r.choice(N, 300, replace=False)
+    mean, var = f.predict(0, X[idx])
+    assert np.all(np.isfinite(mean)) and np.all(var >= 0.0) and np.all(var <= 1.0 + 1e-12)
+    assert np.max(np.abs(mean - y[idx])) <= 0.5 and np.max(var) <= 1e-2          # dense data: posterior hugs the observations
+    far = np.full((1, d), 50.0)
+    m_far, v_far = f.predict(0, far)
+    assert abs(m_far[0] - hyp[0, 4]) <= 1e-12 and abs(v_far[0] - 1.0) <= 1e-12      # no correlation left: the prior
+    f.free()
+
+
+def test_int8_path_at_its_largest_size_matches_the_fp64_path(ctx, oracle):
+    # N = 16384: the longest int32 accumulations the INT8 kernels are allowed to run (posterior k = 16384, inversion
+    # k = 8192); inverse and posterior against the all-FP64 path on the same problem
+    N, d = 16384, 3
+    r = np.random.default_rng(3)
+    X = oracle.sobol_points(d, N)
+    y = oracle.ackley(X)
+    y = (y - y.mean()) / y.std()
+    hyp = np.array([[np.log(0.2), np.log(0.3), np.log(0.25), 0.1, 0.5 * np.log(1e-2), 0.05]])
+    Xc = r.random((500, d))
+    keep = ctx.posterior_path()
+    out = {}
+    try:
+        for path in (L.PATH_FP64_DMMA, L.PATH_INT8_OZAKI):
+            ctx.set_posterior_path(path)
+            f = models.GPFactors(X, y, hyp)
+            assert f.info[0] == 0
+            out[path] = (f.logml[0],) + f.predict(0, Xc)
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
+    a, b = out[L.PATH_FP64_DMMA], out[L.PATH_INT8_OZAKI]
+    sf2 = np.exp(2 * hyp[0, 3])
+    assert a[0] == b[0]                                               # single factor: the same FP64 factorisation
+    # cond(K) ~ N sf2 / sn2 = 2e6 and |alpha| ~ 1e2: any two fp64 algorithms differ by ~1e-8 in the mean here
+    dm, dv = np.max(np.abs(a[1] - b[1])), np.max(np.abs(a[2] - b[2])) / sf2
+    print("N = 16384, int8 vs fp64 path: max |mean diff| %.2e, max |var diff| / sf2 %.2e" % (dm, dv))
+    assert dm <= 5e-8 and dv <= 1e-9
+    assert np.all(b[2] >= 0) and np.all(b[2] <= sf2 * (1 + 1e-12))
+    ref = oracle.gp_fit(X, y, hyp[0], 0)
+    m_ref, v_ref = oracle.gp_predict(ref, Xc[:40])
+    for mv in (a, b):
+        assert np.max(np.abs(mv[1][:40] - m_ref)) <= 1e-7 and np.max(np.abs(mv[2][:40] - v_ref)) <= 1e-8 * sf2
+
+
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
     Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 3, 2000, 1e-2)
     a = models.GPFactors(Xo, y, hyp)
