@@ -657,7 +657,7 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
     int8_t* ksS = reinterpret_cast<int8_t*>(ctx->ks);
     {
       StageTimer t(ctx, ST_KSTAR);
-      B7_CHECK(b7_i8_cov_slices(ctx, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau, ksS));
+      B7_CHECK(b7_i8_cov_slices(ctx, ctx->stream, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau, ksS));
       t.stop(1);
     }
     B7_CHECK(grow(ctx, &ctx->i8_partial, &ctx->i8_partial_bytes, b7_i8_partial_bytes(gp->Np, rp64)));
@@ -764,6 +764,8 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
   for (int64_t c0 = 0; c0 < count && rc == 0; c0 += P) {
     const int64_t n = std::min(P, count - c0), np = pad128(n);
     double* dm = ctx->moments; double* dv = ctx->moments + (size_t)S * np;
+    // (running the K* pass of draw s + 1 on a second stream under the posterior pass of draw s was tried: no gain,
+    // the power cap hands the time back)
     for (int s = 0; s < S && rc == 0; ++s)
       rc = posterior_panel(gp, s, grid->X + (row0 + c0) * grid->d, n, dm + (size_t)s * np, dv + (size_t)s * np);
     if (rc < 0) break;

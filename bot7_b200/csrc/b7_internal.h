@@ -149,8 +149,8 @@ int b7_launch_trtri_i8(b7_gp* gp, int s0, int count);
 #define B7_I8_SLICES 7        // radix-256 digit slices per operand
 #define B7_I8_MAX_NP 16384    // 7 products x 2^14 x Np must stay below 2^31
 int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count);
-int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
-                     const double* par, double tau, int8_t* ksS);
+int b7_i8_cov_slices(b7_ctx* ctx, cudaStream_t st, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt,
+                     int N, int Np, const double* par, double tau, int8_t* ksS);
 int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
                            const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
                            int64_t cols_pad, double tau, double sf2, double mconst, double* partial, double* mean, double* var);

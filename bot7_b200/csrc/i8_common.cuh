@@ -20,6 +20,12 @@ __device__ __forceinline__ unsigned long long digit_bytes(double t) {
   return (unsigned long long)(x + 0x0000808080808080LL) ^ 0x0000808080808080ULL;
 }
 
+// same for a value that already carries the factor 2^54
+__device__ __forceinline__ unsigned long long digit_bytes_scaled(double t54) {
+  const long long x = __double2ll_rn(t54);
+  return (unsigned long long)(x + 0x0000808080808080LL) ^ 0x0000808080808080ULL;
+}
+
 // digit bytes of 4 consecutive k -> one 32-bit word per slice (byte j = element j): two 4 x 4 byte transposes
 __device__ __forceinline__ void pack4(const unsigned long long (&z)[4], uint32_t (&w)[NS]) {
   const uint32_t l0 = (uint32_t)z[0], l1 = (uint32_t)z[1], l2 = (uint32_t)z[2], l3 = (uint32_t)z[3];

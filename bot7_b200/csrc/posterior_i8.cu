@@ -80,8 +80,10 @@ slice_factor_kernel(const double* __restrict__ fac, long long fac_stride, int Np
 }
 
 // K(X*, X) evaluated and sliced in one pass: ksS[ct][ks][q][kc][cand 64][16]; one block per (candidate tile, 64 columns)
+// 128 threads, two 16-column chunks each (21.6 -> 16.9 ms per step against 256 threads x one chunk, together with
+// folding sf2 / tau * 2^54 into one factor).
 template <int DT, int KERNEL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const double* __restrict__ Xt, int N, int Np,
                   const double* __restrict__ par, double inv_tau, int8_t* __restrict__ ksS) {
   __shared__ double s_x[DT][64];
@@ -89,8 +91,8 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
   __shared__ double s_tab[64];
   if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
   const int ct = blockIdx.x, kb64 = blockIdx.y, KS_ALL = Np / KB;
-  const int c = threadIdx.x & 63, kc = threadIdx.x >> 6;          // warp = 32 consecutive candidates, one k chunk
-  for (int e = threadIdx.x; e < DT * 64; e += 256) {
+  const int c = threadIdx.x & 63;                                 // warp = 32 consecutive candidates, one k chunk
+  for (int e = threadIdx.x; e < DT * 64; e += 128) {
     const int i = e / 64, k = kb64 * 64 + e % 64;
     s_x[i][e % 64] = (i < d && k < N) ? Xt[(long long)i * Np + k] : 0.0;
   }
@@ -100,7 +102,11 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
   double a[DT];
 #pragma unroll
   for (int i = 0; i < DT; ++i) a[i] = (row < rows && i < d) ? A[row * d + i] : 0.0;
-  const double sf2 = par[B7_MAX_DIMS];
+  // sf2 / tau * 2^54: tau is a power of two, so scaling sf2 first rounds exactly like scaling the product afterwards
+  const double sf2s = par[B7_MAX_DIMS] * inv_tau * 18014398509481984.0;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+  const int kc = (threadIdx.x >> 6) + 2 * half;
   uint32_t pk[4][NS];
   unsigned long long z[4];
 #pragma unroll
@@ -115,19 +121,20 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
         r2 = fma(t, t, r2);
       }
       if (KERNEL == B7_KERNEL_ARDSE) {
-        val = sf2 * exp_neg(-0.5 * r2, s_tab);
+        val = sf2s * exp_neg(-0.5 * r2, s_tab);
       } else {
         const double rr = sqrt(r2), s5r = 2.23606797749978969641 * rr;
-        val = sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp_neg(-s5r, s_tab));
+        val = sf2s * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp_neg(-s5r, s_tab));
       }
     }
-    z[i & 3] = digit_bytes(val * inv_tau);
+    z[i & 3] = digit_bytes_scaled(val);
     if ((i & 3) == 3) pack4(z, pk[i >> 2]);
   }
   const int gkc = kb64 * 4 + kc, ks = gkc / KC, kcc = gkc % KC;
   int8_t* dst = ksS + ((long long)ct * KS_ALL + ks) * B_STAGE + kcc * (TN * 16) + c * 16;
 #pragma unroll
   for (int p = 0; p < NS; ++p) *reinterpret_cast<uint4*>(dst + p * (KC * TN * 16)) = make_uint4(pk[0][p], pk[1][p], pk[2][p], pk[3][p]);
+  }
 }
 
 // sum over the 32 lanes of x[j] for every j, result for column j lands in lane j (transpose-reduce butterfly)
@@ -354,27 +361,27 @@ int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, dou
 }
 
 template <int DT>
-static int launch_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N,
-                             int Np, const double* par, double inv_tau, int8_t* ksS) {
+static int launch_cov_slices(b7_ctx* ctx, cudaStream_t st, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d,
+                             const double* Xt, int N, int Np, const double* par, double inv_tau, int8_t* ksS) {
   dim3 grid((unsigned)(rows_pad / TN), Np / 64);
-  if (kernel == B7_KERNEL_ARDSE) cov_slices_kernel<DT, B7_KERNEL_ARDSE><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
-  else cov_slices_kernel<DT, B7_KERNEL_MATERN52><<<grid, 256, 0, ctx->stream>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
+  if (kernel == B7_KERNEL_ARDSE) cov_slices_kernel<DT, B7_KERNEL_ARDSE><<<grid, 128, 0, st>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
+  else cov_slices_kernel<DT, B7_KERNEL_MATERN52><<<grid, 128, 0, st>>>(A, rows, d, Xt, N, Np, par, inv_tau, ksS);
   b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;
 }
 
-int b7_i8_cov_slices(b7_ctx* ctx, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt, int N, int Np,
-                     const double* par, double tau, int8_t* ksS) {
+int b7_i8_cov_slices(b7_ctx* ctx, cudaStream_t st, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt,
+                     int N, int Np, const double* par, double tau, int8_t* ksS) {
   if (rows_pad <= 0) return 0;
   const double inv_tau = 1.0 / tau;
-  if (d <= 2) return launch_cov_slices<2>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  if (d <= 4) return launch_cov_slices<4>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  if (d <= 6) return launch_cov_slices<6>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  if (d <= 8) return launch_cov_slices<8>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  if (d <= 16) return launch_cov_slices<16>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  if (d <= 24) return launch_cov_slices<24>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
-  return launch_cov_slices<40>(ctx, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 2) return launch_cov_slices<2>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 4) return launch_cov_slices<4>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 6) return launch_cov_slices<6>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 8) return launch_cov_slices<8>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 16) return launch_cov_slices<16>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  if (d <= 24) return launch_cov_slices<24>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
+  return launch_cov_slices<40>(ctx, st, kernel, A, rows, rows_pad, d, Xt, N, Np, par, inv_tau, ksS);
 }
 
 size_t b7_i8_partial_bytes(int Np, int64_t cols_pad) { return (size_t)(cols_pad / TN) * (Np / TM) * TN * 2 * sizeof(double); }
