@@ -402,7 +402,8 @@ def main():
                       "inversion_for_predict_S32": fit_ms["trtri_ms"], **{k: v for k, v in fit_ms.items() if k.endswith("_ms")}},
         "e2e": {"value": world * cnt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "includes": "b7_gp_fit from host X/y/hyp (K build, batched potrf, inversion) + b7_grid_from_host + b7_acq_score "
-                            "with the score vector copied back; median of 3 steps after 2 untimed ones", "seconds_per_step": e2e_s},
+                            "with the score vector copied back; median of 3 steps after 2 untimed ones", "seconds_per_step": e2e_s,
+                "all_steps_s": [round(x, 4) for x in e2e_times]},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,
         "clocks": clocks, "roofline": roofline, "stages": stages,
         "posterior_path": path_name[default_path],

@@ -30,18 +30,61 @@ constexpr double kLog2Pi = 1.83787706640934548356;
 // b7_init): buffers freed by one fit are handed back to the next without a driver round trip
 // (a fresh cudaMalloc of the 4.3 GB factor array costs tens of ms; the reference allocates and
 // garbage-collects on every call, bots/bayesopt.lua:77).
-template <typename T>
-int dev_alloc(b7_ctx* ctx, T** p, size_t count) {
+constexpr size_t kCacheMin = (size_t)1 << 20;
+
+void cache_flush(b7_ctx* ctx) {
+  for (const b7_ctx::Block& b : ctx->cache) cudaFreeAsync(b.p, ctx->stream);
+  ctx->cache.clear();
+  ctx->cache_bytes = 0;
+}
+
+int dev_alloc_bytes(b7_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
-  if (count == 0) count = 1;
-  cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes == 0) bytes = 256;
+  if (bytes >= kCacheMin)
+    for (size_t i = 0; i < ctx->cache.size(); ++i)
+      if (ctx->cache[i].bytes == bytes) {                 // the same request as an earlier fit: same block
+        *p = ctx->cache[i].p;
+        ctx->cache_bytes -= bytes;
+        ctx->cache[i] = ctx->cache.back();
+        ctx->cache.pop_back();
+        ctx->live[*p] = bytes;
+        return 0;
+      }
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess && !ctx->cache.empty()) {          // give the cached blocks back and try again
+    cudaGetLastError();
+    cache_flush(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(p, bytes, ctx->stream);
+  }
   if (e != cudaSuccess) {
-    b7_set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaGetLastError();
+    b7_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     return B7_ERR_NOMEM;
   }
+  if (bytes >= kCacheMin) ctx->live[*p] = bytes;
   return 0;
 }
-inline void dev_free(b7_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+template <typename T>
+int dev_alloc(b7_ctx* ctx, T** p, size_t count) { return dev_alloc_bytes(ctx, (void**)p, (count ? count : 1) * sizeof(T)); }
+
+inline void dev_free(b7_ctx* ctx, void* p) {
+  if (!p) return;
+  auto it = ctx->live.find(p);
+  if (it != ctx->live.end()) {
+    const size_t bytes = it->second;
+    ctx->live.erase(it);
+    if (ctx->cache_bytes + bytes <= ctx->cache_cap) {
+      ctx->cache.push_back({p, bytes});
+      ctx->cache_bytes += bytes;
+      return;
+    }
+  }
+  cudaFreeAsync(p, ctx->stream);
+}
 
 int grow(b7_ctx* ctx, double** p, size_t* have, size_t need_bytes) {
   if (*have >= need_bytes) return 0;
@@ -180,6 +223,7 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
   B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  { size_t free_b = 0, total_b = 0; B7_CUDA(cudaMemGetInfo(&free_b, &total_b)); ctx->cache_cap = total_b / 3; }
   { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_POTRF_I8"); ctx->potrf_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_TRTRI_I8"); ctx->trtri_i8 = !(e && e[0] == '0'); }
@@ -199,6 +243,7 @@ void b7_shutdown(b7_ctx* ctx) {
   dev_free(ctx, ctx->moments);
   dev_free(ctx, ctx->xs_stage);
   dev_free(ctx, ctx->i8_partial);
+  cache_flush(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->stream2);
   { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
