@@ -109,3 +109,22 @@ def blockrec_inverse(L, blk):
             X[(r0 + nb) * blk:(r0 + nb + n2) * blk, r0 * blk:(r0 + nb) * blk] = out
         nb *= 2
     return X
+
+
+# ---- work items of the persistent INT8 posterior kernel (struct Walk in posterior_i8.cu) --------------------
+
+def walk_items(NB, chunk, group, n_tiles):
+    """[(tile, [row blocks])] in issue order: groups of `group` tiles, inside a group pair level then tile; pair level
+    l takes row-block chunks l and cpt - 1 - l (one chunk when they coincide)."""
+    cpt = (NB + chunk - 1) // chunk
+    npl = (cpt + 1) // 2
+    items = []
+    for item in range(n_tiles * npl):
+        g = min(item // (group * npl), (n_tiles - 1) // group)
+        g_tiles = min(group, n_tiles - g * group)
+        within = item - g * group * npl
+        tile, level = g * group + within % g_tiles, within // g_tiles
+        parts = [level] if 2 * level == cpt - 1 else [level, cpt - 1 - level]
+        rbs = [rb for c in parts for rb in range(c * chunk, min(NB, (c + 1) * chunk))]
+        items.append((tile, rbs))
+    return items

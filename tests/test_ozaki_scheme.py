@@ -85,3 +85,21 @@ def test_block_recursive_inverse_for_any_number_of_blocks(NB):
             covered += list(range(pair * 2 * nb, min(NB, pair * 2 * nb + nb))) + list(range(pair * 2 * nb + nb, pair * 2 * nb + nb + n2))
         assert covered == list(range(NB))
         nb *= 2
+
+
+@pytest.mark.parametrize("NB,chunk,group,n_tiles", [(32, 2, 16, 296), (32, 4, 16, 296), (1, 1, 16, 5), (5, 2, 16, 40), (18, 2, 16, 33),
+                                                     (128, 2, 16, 7), (7, 1, 3, 10), (12, 32, 16, 100)])
+def test_posterior_work_items_cover_every_row_block_once(NB, chunk, group, n_tiles):
+    chunk = min(chunk, NB)
+    items = oz.walk_items(NB, chunk, group, n_tiles)
+    seen = sorted((t, rb) for t, rbs in items for rb in rbs)
+    assert seen == [(t, rb) for t in range(n_tiles) for rb in range(NB)]
+    # weight of an item = stages streamed = sum (rb + 1): equal for all items when the chunks pair up evenly
+    w = [sum(rb + 1 for rb in rbs) for _, rbs in items]
+    cpt = (NB + chunk - 1) // chunk
+    if NB % chunk == 0 and cpt % 2 == 0:
+        assert len(set(w)) == 1
+    # tiles of at most two groups are in flight among any 148 consecutive items when a group-level fills the machine
+    if len(items) >= 148 and group * ((cpt + 1) // 2) >= 128:
+        for i in range(0, len(items) - 148, 37):
+            assert len({t // group for t, _ in items[i:i + 148]}) <= 3
