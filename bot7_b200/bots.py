@@ -117,11 +117,15 @@ class abstract:
     def nominate(self):
         print("Error: nominate() method not implemented")
 
+    def class_(self):
+        """bots/abstract.lua:246-252: torch.type(self)."""
+        return "bot7.bots." + self.__class__.__name__
+
     def save(self, path=None):
         """bots/abstract.lua:234-240: torch.save('demo_<class>.t7', {best=, x=observed, y=responses}), same file format."""
         best = {k: (np.asarray(v, dtype=np.float64) if isinstance(v, np.ndarray) else v) for k, v in self.best.items()}
         results = {"best": best, "x": self.observed, "y": self.responses}
-        path = path or "demo_%s.t7" % self.__class__.__name__
+        path = path or "demo_%s.t7" % self.class_()
         t7.save(path, results)
         return path
 

@@ -105,3 +105,20 @@ def test_cache_from_results_feeds_the_bot_cache_protocol(tmp_path):
         bots.cache_from_results({"best": {}})
     with pytest.raises(ValueError, match="5 observed points but 4 responses"):
         bots.cache_from_results({"x": res["x"], "y": res["y"][:4]})
+
+
+def test_bot_save_writes_the_reference_file_name_and_layout(tmp_path, monkeypatch):
+    # bots/abstract.lua:234-240: torch.save('demo_' .. torch.type(self) .. '.t7', {best=, x=, y=}); no device needed
+    from bot7_b200 import bots
+    r = np.random.default_rng(2)
+    bot = object.__new__(bots.random_search)
+    bot.observed, bot.responses = r.random((4, 3)), r.random((4, 1))
+    bot.best = {"x": bot.observed[2:3], "y": bot.responses[2:3], "t": 3}
+    monkeypatch.chdir(tmp_path)
+    path = bot.save()
+    assert path == "demo_bot7.bots.random_search.t7" and (tmp_path / path).exists()
+    res = t7.load(str(tmp_path / path))
+    assert list(res) == ["best", "x", "y"] and list(res["best"]) == ["x", "y", "t"] and res["best"]["t"] == 3.0
+    assert np.array_equal(res["x"], bot.observed) and np.array_equal(res["y"], bot.responses)
+    cache = bots.cache_from_results(res)
+    assert np.array_equal(cache["observed"], bot.observed) and cache["responses"].shape == (4, 1)
