@@ -43,15 +43,16 @@ def row_scale(a):
     return np.where(mx > 0, np.ldexp(1.0, e), 1.0)
 
 
-def sliced_product(A, B):
-    """A [M, K] (row operand), B [N, K] (column operand) -> (V, classes, V_full)
+def sliced_product(A, B, sb=None):
+    """A [M, K] (row operand), B [N, K] (column operand; sb: its scales, default one per row of B) -> (V, classes, ...)
 
     V       float64 [M, N]: what the kernels return, sigma_i tau_j sum_w 2^(4-8w) S_w with the 7 class sums S_w of the
             28 kept slice pairs (combined here exactly and rounded once);
     classes int64 [7, M, N]: the class sums (must fit int32);
     V_full  exact product of the ROUNDED operands as Python integers scaled by 2^108 (object array), for error bounds.
     """
-    sa, sb = row_scale(A), row_scale(B)
+    sa = row_scale(A)
+    sb = row_scale(B) if sb is None else np.broadcast_to(np.asarray(sb, dtype=np.float64), (B.shape[0],)).copy()
     da, db = digits(A / sa[:, None]), digits(B / sb[:, None])
     M, N = A.shape[0], B.shape[0]
     classes = np.zeros((NS, M, N), dtype=np.int64)

@@ -103,3 +103,32 @@ def test_posterior_work_items_cover_every_row_block_once(NB, chunk, group, n_til
     if len(items) >= 148 and group * ((cpt + 1) // 2) >= 128:
         for i in range(0, len(items) - 148, 37):
             assert len({t // group for t, _ in items[i:i + 148]}) <= 3
+
+
+def test_sliced_posterior_of_a_small_gp_meets_the_parity_tolerance():
+    # the whole INT8 posterior in exact integers on the CPU: V = L^-1 K*^T through 7 x 7 slices and 28 products (one power
+    # of two tau > sf2 for K*, one per row of L^-1), var = sf2 - colsumsq(V), mean = m + V^T beta, against the oracle
+    import scipy.linalg as sla
+    import b7_oracle as o
+    N, d, M = 300, 6, 40
+    r = np.random.default_rng(8)
+    X = o.sobol_points(d, N + M)
+    Xo, Xc = X[:N], X[N:]
+    y = o.hartmann6(Xo)
+    y = (y - y.mean()) / y.std()
+    hyp = np.concatenate([np.log(0.1) + r.random(d) * (np.log(2) - np.log(0.1)), [0.2, 0.5 * np.log(1e-3), 0.05]])
+    fit = o.gp_fit(Xo, y, hyp, 0)
+    m_ref, v_ref = o.gp_predict(fit, Xc)
+    Linv = sla.solve_triangular(fit["L"], np.eye(N), lower=True)
+    Ks = o.kernel_matrix(Xc, Xo, fit["w"], fit["sf2"], fit["kernel"]) if hasattr(o, "kernel_matrix") else None
+    if Ks is None:                                                     # ARD-SE by hand (oracle/SPEC.md)
+        D = (Xc[:, None, :] - Xo[None, :, :]) * fit["w"][None, None, :]
+        Ks = fit["sf2"] * np.exp(-0.5 * np.sum(D * D, axis=2))
+    tau = np.ldexp(1.0, np.frexp(fit["sf2"])[1])
+    V, classes, _, _, _, _ = oz.sliced_product(Linv, Ks, sb=tau)      # V[i, c] = (L^-1 k*_c)_i
+    assert np.abs(classes).max() < 2 ** 31
+    beta = sla.solve_triangular(fit["L"], y - fit["m"], lower=True)
+    var = fit["sf2"] - np.sum(V * V, axis=0)
+    mean = fit["m"] + V.T @ beta
+    assert np.max(np.abs(var - v_ref)) <= 1e-12 * fit["sf2"] and np.max(np.abs(mean - m_ref)) <= 1e-11
+    assert np.max(np.abs(var - v_ref) / v_ref) <= 1e-9                # the tolerance of BASELINE.json's north star
