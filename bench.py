@@ -4,11 +4,13 @@
 metric : EI candidates scored per second at N_obs = 4096, S = 32 hyper-parameter draws
          (Hartmann6, d = 6, ARD-SE GP), plus GP fit ms (K build + batched Cholesky) beside it.
 step   : one pass of the hot path over one batch of M candidates per GPU: for every draw the K*
-         tile, the posterior (TRMM on FP64 DMMA tiles), then the fused EI + S-average + argmax pass,
-         and (N > 1) the all-gather of the per-rank (best, index, nan) triples.
+         tile, the posterior (V = L^-1 K*^T: exact int8 slice products on tcgen05 by default, FP64 DMMA
+         tiles timed beside it), then the fused EI + S-average + argmax pass, and (N > 1) the
+         all-gather of the per-rank (best, index, nan) triples.
 value  : whole-job candidates/s with the S fitted factors and the candidate grid resident in HBM.
 e2e    : the same acquisition through the C ABI with HOST buffers: b7_gp_fit (X, y, hyp from the
-         host), b7_grid_from_host (H2D of the batch), b7_acq_score with the score vector read back.
+         host), b7_grid_from_host (H2D of the batch), b7_acq_score with the score vector read back;
+         median of 3 steps after 2 untimed ones.
 Launch : python bench.py --gpus N --steps K --warmup W   (torchrun for N > 1, one rank per GPU).
          python bench.py --impl reference ...            (CPU arm: the oracle port on the host cores)
 Prints ONE JSON line on rank 0.
