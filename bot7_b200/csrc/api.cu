@@ -227,6 +227,7 @@ int b7_init(int device, b7_ctx** out) {
   { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_POTRF_I8"); ctx->potrf_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_TRTRI_I8"); ctx->trtri_i8 = !(e && e[0] == '0'); }
+  { const char* e = getenv("B7_POST_PAIR"); ctx->post_pair = !(e && e[0] == '0') && ctx->sm_count >= 2; }
   B7_CUDA(cudaEventCreate(&ctx->ev0));
   B7_CUDA(cudaEventCreate(&ctx->ev1));
   B7_CUDA(cudaEventCreate(&ctx->tm0));
@@ -415,7 +416,7 @@ void b7_gp_free(b7_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
-  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->tt, gp->logdet, gp->info};
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->alpha, gp->tt, gp->logdet, gp->info};
   for (void* p : ptrs) dev_free(gp->ctx, p);
   delete gp;
 }
@@ -542,9 +543,8 @@ static bool i8_path(const b7_gp* gp) { return gp->ctx->use_i8 && gp->Np <= B7_I8
 // INT8 path: slice L^-1 (allocated on first use)
 static int gp_slice(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
-  const size_t fs = (size_t)gp->Np * gp->Np;
   if (!gp->facS) {
-    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * fs * B7_I8_SLICES));
+    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * b7_i8_facs_stride(gp->Np)));
     B7_CHECK(dev_alloc(ctx, &gp->sigma, (size_t)gp->S * gp->Np));
   }
   B7_CHECK(b7_i8_slice_factor(ctx, gp->fac, gp->Np, gp->facS, gp->sigma, s0, count));
@@ -556,6 +556,8 @@ static int gp_invert(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
+  // alpha = L^-T beta while L is still there (the INT8 path's mean is the fp64 dot product k*^T alpha)
+  if (gp->Np <= B7_I8_MAX_NP) B7_CHECK(b7_launch_alpha(gp, s0, count, false));
   B7_CHECK(b7_launch_trtri(gp, s0, count));
   for (int s = s0; s < s0 + count; ++s) gp->sliced[s] = 0;
   if (i8_path(gp)) B7_CHECK(gp_slice(gp, s0, count));
@@ -569,6 +571,7 @@ int b7_gp_mark_ready(b7_gp* gp) {
   std::fill(gp->sliced.begin(), gp->sliced.end(), 0);
   if (i8_path(gp)) {
     B7_CUDA(cudaSetDevice(gp->ctx->device));
+    B7_CHECK(b7_launch_alpha(gp, 0, gp->S, true));      // the factors arrive inverted: alpha = (L^-1)^T beta
     B7_CHECK(gp_slice(gp, 0, gp->S));
     B7_CUDA(cudaStreamSynchronize(gp->ctx->stream));
   }
@@ -597,7 +600,8 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
   if ((rc = dev_alloc(ctx, &gp->X, (size_t)N * d)) || (rc = dev_alloc(ctx, &gp->Xt, (size_t)d * Np)) || (rc = dev_alloc(ctx, &gp->y, (size_t)N)) ||
       (rc = dev_alloc(ctx, &gp->par, (size_t)S * kParStride)) || (rc = dev_alloc(ctx, &gp->fac, (size_t)S * fs)) ||
       (rc = dev_alloc(ctx, &gp->dinv, (size_t)S * ds)) || (rc = dev_alloc(ctx, &gp->dinvT, (size_t)S * ds)) ||
-      (rc = dev_alloc(ctx, &gp->beta, (size_t)S * Np)) || (rc = dev_alloc(ctx, &gp->tt, (size_t)S * B7_NB * Np)) ||
+      (rc = dev_alloc(ctx, &gp->beta, (size_t)S * Np)) || (rc = dev_alloc(ctx, &gp->alpha, (size_t)S * Np)) ||
+      (rc = dev_alloc(ctx, &gp->tt, (size_t)S * B7_NB * Np)) ||
       (rc = dev_alloc(ctx, &gp->logdet, (size_t)S)) || (rc = dev_alloc(ctx, &gp->info, (size_t)S)))
     return fail(rc);
   gp->y_host.assign(y, y + N);
@@ -700,16 +704,17 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
     const double tau = ldexp(1.0, e);
     const int64_t rp64 = (rows + 63) / 64 * 64;
     int8_t* ksS = reinterpret_cast<int8_t*>(ctx->ks);
+    B7_CHECK(grow(ctx, &ctx->i8_partial, &ctx->i8_partial_bytes, b7_i8_partial_bytes(gp->Np, rp64)));
     {
       StageTimer t(ctx, ST_KSTAR);
-      B7_CHECK(b7_i8_cov_slices(ctx, ctx->stream, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau, ksS));
+      B7_CHECK(b7_i8_cov_slices(ctx, ctx->stream, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau,
+                                gp->alpha + (size_t)s * gp->Np, ksS, b7_i8_mean_partials(ctx->i8_partial, gp->Np, rp64)));
       t.stop(1);
     }
-    B7_CHECK(grow(ctx, &ctx->i8_partial, &ctx->i8_partial_bytes, b7_i8_partial_bytes(gp->Np, rp64)));
     StageTimer t(ctx, ST_POSTERIOR);
-    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * gp->Np * gp->Np * B7_I8_SLICES, gp->sigma + (size_t)s * gp->Np,
-                                    gp->beta + (size_t)s * gp->Np, gp->Np, ksS, A, rows, gp->d, gp->Xt, gp->par + (size_t)s * kParStride,
-                                    gp->kernel, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2], ctx->i8_partial, mean, var));
+    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * b7_i8_facs_stride(gp->Np), gp->sigma + (size_t)s * gp->Np, gp->Np, ksS, A, rows,
+                                    gp->d, gp->Xt, gp->par + (size_t)s * kParStride, gp->kernel, rp64, tau, p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2],
+                                    ctx->i8_partial, mean, var));
     t.stop(1);   // one posterior pass (the few-microsecond finish kernel rides along)
     return 0;
   }

@@ -44,6 +44,7 @@ struct b7_ctx {
   bool use_i8 = false;           // posterior pass on the INT8 tensor pipe (posterior_i8.cu); default on, B7_POSTERIOR_I8=0 turns it off
   bool potrf_i8 = true;          // with use_i8: also the k = 512 trailing updates of the Cholesky (B7_POTRF_I8=0: FP64 DMMA)
   bool trtri_i8 = true;          // with use_i8: also the inversion of the factors (B7_TRTRI_I8=0: FP64 DMMA sweep)
+  bool post_pair = true;         // INT8 posterior pass on CTA pairs (tcgen05 cta_group::2); B7_POST_PAIR=0: one CTA per tile
   int64_t launches = 0;
   // scratch for the posterior pass (grown on demand)
   double* ks = nullptr;        // K* panel, [panel_rows][Np]
@@ -85,7 +86,8 @@ struct b7_gp {
   std::vector<double> par_host;
   std::vector<double> y_host;   // observations kept on the host for the residual upload of refits / retries
   double* fac = nullptr;    // device S x Np x Np : K -> L -> L^-1, lower, in the tiled (fragment-order) layout
-  int8_t* facS = nullptr;   // device S x Np x Np x B7_I8_SLICES : int8 slices of L^-1 (only with ctx->use_i8)
+  int8_t* facS = nullptr;   // device S x b7_i8_facs_stride(Np) : int8 slices of L^-1, pair-packed lower block triangle (only with ctx->use_i8)
+  double* alpha = nullptr;  // device S x Np : L^-T beta = K_y^-1 (y - m) (the INT8 path's mean is m + k*^T alpha in fp64)
   double* sigma = nullptr;  // device S x Np : per-row power-of-two scales of the slices
   double* dinv = nullptr;   // device S x NB x (128 x 128 tiled) : inverse of the diagonal blocks of L
   double* dinvT = nullptr;  // device, transposes of dinv (tiled)
@@ -141,6 +143,7 @@ int b7_launch_cov_batched(b7_ctx* ctx, int kernel, const double* A /* rows x d *
 // potrf.cu
 int b7_launch_potrf(b7_gp* gp, int s0, int count);      // K -> L, beta, logdet, info for draws [s0,s0+count)
 int b7_launch_trtri(b7_gp* gp, int s0, int count);      // L -> L^-1 in place
+int b7_launch_alpha(b7_gp* gp, int s0, int count, bool from_inverse);   // alpha = L^-T beta (from L, or from L^-1)
 // posterior.cu
 int b7_launch_untile(b7_ctx* ctx, const double* facT, double* out /* N x N row-major */, int Np, int N);
 int b7_launch_posterior(b7_ctx* ctx, const double* LinvT /* tiled */, const double* beta, int Np, const double* ksT /* tiled */,
@@ -156,13 +159,15 @@ int b7_launch_trtri_i8(b7_gp* gp, int s0, int count);
 // posterior_i8.cu
 #define B7_I8_SLICES 7        // radix-256 digit slices per operand
 #define B7_I8_MAX_NP 16384    // 7 products x 2^14 x Np must stay below 2^31
+size_t b7_i8_facs_stride(int Np);       // bytes of the pair-packed slice array of one draw
 int b7_i8_slice_factor(b7_ctx* ctx, const double* fac, int Np, int8_t* facS, double* sigma, int s0, int count);
 int b7_i8_cov_slices(b7_ctx* ctx, cudaStream_t st, int kernel, const double* A, int64_t rows, int64_t rows_pad, int d, const double* Xt,
-                     int N, int Np, const double* par, double tau, int8_t* ksS);
-int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, const double* beta, int Np, const int8_t* ksS,
-                           const double* cand, int64_t rows, int d, const double* Xt, const double* par, int kernel,
-                           int64_t cols_pad, double tau, double sf2, double mconst, double* partial, double* mean, double* var);
-size_t b7_i8_partial_bytes(int Np, int64_t cols_pad);   // scratch of the launch above: per-row-block partial sums
+                     int N, int Np, const double* par, double tau, const double* alpha, int8_t* ksS, double* meanP);
+int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma, int Np, const int8_t* ksS, const double* cand,
+                           int64_t rows, int d, const double* Xt, const double* par, int kernel, int64_t cols_pad, double tau,
+                           double sf2, double mconst, double* partial, double* mean, double* var);
+size_t b7_i8_partial_bytes(int Np, int64_t cols_pad);   // scratch of the two launches above: sum v^2 and mean partials
+double* b7_i8_mean_partials(double* partial, int Np, int64_t cols_pad);
 // score.cu
 int b7_launch_score(b7_ctx* ctx, int kind, const double* mean, const double* var, int S, int64_t M, int64_t ld,
                     double tradeoff, int bound, double sign, double fmin, const int64_t* removed, int64_t n_removed,

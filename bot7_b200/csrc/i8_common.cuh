@@ -90,6 +90,61 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// ---- CTA pairs (tcgen05 cta_group::2) --------------------------------------------------------------------
+// One instruction of the leader CTA drives the tensor cores of both SMs of a cluster of two: M = 256 (CTA c owns rows
+// 128 c .. 128 c + 127 of A and of D, in its own shared memory / TMEM), B is split by rows of the N dimension (CTA c
+// holds columns N/2 c .. of the output), and both shared memories are read at the same offsets.
+template <int HINT>
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+#define B7_UMMA_I8P(QUAL)                                                                                           \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t}\n" \
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory")
+  if (HINT == 1) B7_UMMA_I8P(".collector::a::fill");
+  else if (HINT == 2) B7_UMMA_I8P(".collector::a::use");
+  else if (HINT == 3) B7_UMMA_I8P(".collector::a::lastuse");
+  else B7_UMMA_I8P("");
+#undef B7_UMMA_I8P
+}
+// completion of every MMA issued so far by this thread -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// one arrival on the barrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(
+                   smem_u32(bar)),
+               "r"(cta)
+               : "memory");
+}
+// wait with cluster-scope acquire (the arrivals may come from the peer CTA) and a watchdog: a protocol error turns
+// into a trap after ~2 s instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+  uint32_t ok = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (ok) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 2000000000ULL) __trap();
+  }
+}
+
 // ---- slicing kernels: 512 threads = 128 rows (or columns) x 4 interleaved k quarters --------------------------
 constexpr int SLICE_THREADS = 512;
 

@@ -381,6 +381,77 @@ int set_attrs(int device) {
   return 0;
 }
 
+// ---- alpha = L^-T beta ------------------------------------------------------------------------------
+// The INT8 posterior path takes the mean from an fp64 dot product k*^T alpha (the arithmetic the oracle uses,
+// `Ks @ alpha`) instead of v^T beta through the sliced operands, so alpha is needed once per fit.  Blocked back
+// substitution on the factor before it is inverted in place: column sweep from the bottom, one CTA per draw,
+//   alpha_ib = inv(L_ib,ib)^T r_ib ;   r[k] -= sum_row L[ib*128 + row][k] alpha_ib[row]   for k < 128 ib.
+// Row block ib of L is one contiguous run of tiles; a warp owns a k-group (128 rows x 4 columns = 4 KB), lanes are
+// rows, and the 4 column sums come out of a fixed shuffle tree (deterministic).
+// FROM_INVERSE: fac already holds L^-1 (the path was switched after the fit, or the factor came from another
+// rank): alpha = (L^-1)^T beta, the same row-block primitive without the solve.
+constexpr int ALPHA_THREADS = 1024;
+
+template <bool FROM_INVERSE>
+__global__ void __launch_bounds__(ALPHA_THREADS, 1)
+alpha_kernel(const double* __restrict__ fac, long long fac_stride, int Np, const double* __restrict__ dinvT, long long dinv_stride,
+             const double* __restrict__ beta, double* __restrict__ alpha, int s0) {
+  extern __shared__ __align__(16) double sm[];
+  double* r = sm;            // Np
+  double* xa = sm + Np;      // 128
+  const int s = s0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NB = Np / NBK;
+  const double* F = fac + (long long)s * fac_stride;
+  for (int e = tid; e < Np; e += ALPHA_THREADS) r[e] = FROM_INVERSE ? 0.0 : beta[(long long)s * Np + e];
+  __syncthreads();
+  for (int step = 0; step < NB; ++step) {
+    const int ib = FROM_INVERSE ? step : NB - 1 - step;
+    if (tid < NBK) {
+      if (FROM_INVERSE) {
+        xa[tid] = beta[(long long)s * Np + ib * NBK + tid];
+      } else {
+        const double* dt = dinvT + (long long)s * dinv_stride + (long long)ib * NBK * NBK;
+        double sum = 0.0;
+#pragma unroll 4
+        for (int q4 = 0; q4 < NBK / 4; ++q4) {
+          const double4 m = *reinterpret_cast<const double4*>(dt + (q4 >> 2) * TILE_DOUBLES + (q4 & 3) * (BM * 4) + tid * 4);
+          const double* rr = r + ib * NBK + 4 * q4;
+          sum = fma(m.x, rr[0], sum); sum = fma(m.y, rr[1], sum); sum = fma(m.z, rr[2], sum); sum = fma(m.w, rr[3], sum);
+        }
+        xa[tid] = sum;
+        alpha[(long long)s * Np + ib * NBK + tid] = sum;
+      }
+    }
+    __syncthreads();
+    const double* rowblk = F + tile_off(Np / TILE_K, ib, 0);
+    const int n_kg = (FROM_INVERSE ? ib + 1 : ib) * (NBK / 4);       // k-groups of 4 columns left of (or including) the diagonal block
+    for (int kg = warp; kg < n_kg; kg += ALPHA_THREADS / 32) {
+      const double* p = rowblk + (long long)kg * (BM * 4);
+      double4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const double4*>(p + (lane + 32 * i) * 4);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double x = xa[lane + 32 * i];
+        a0 = fma(v[i].x, x, a0); a1 = fma(v[i].y, x, a1); a2 = fma(v[i].z, x, a2); a3 = fma(v[i].w, x, a3);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+      }
+      if (lane == 0) {
+        double* out = r + kg * 4;
+        if (FROM_INVERSE) { out[0] += a0; out[1] += a1; out[2] += a2; out[3] += a3; }
+        else { out[0] -= a0; out[1] -= a1; out[2] -= a2; out[3] -= a3; }
+      }
+    }
+    __syncthreads();
+  }
+  if (FROM_INVERSE)
+    for (int e = tid; e < Np; e += ALPHA_THREADS) alpha[(long long)s * Np + e] = r[e];
+}
+
 }  // namespace
 
 int b7_launch_potrf(b7_gp* gp, int s0, int count) {
@@ -462,6 +533,26 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
       b7_pool_free(ctx, pS[b][1]);
       b7_pool_free(ctx, pSig[b]);
     }
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// alpha = L^-T beta for draws [s0, s0 + count): from L (before the inversion) or from L^-1 (from_inverse)
+int b7_launch_alpha(b7_gp* gp, int s0, int count, bool from_inverse) {
+  b7_ctx* ctx = gp->ctx;
+  const int Np = gp->Np;
+  const size_t smem = (size_t)(Np + NBK) * sizeof(double);
+  if (smem > 200 * 1024) { b7_set_error("alpha: %d observations exceed the shared-memory sweep", Np); return B7_ERR_ARG; }
+  static bool attr[16][2] = {{false}};
+  if (!attr[ctx->device & 15][from_inverse]) {
+    if (from_inverse) B7_CUDA(cudaFuncSetAttribute(alpha_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    else B7_CUDA(cudaFuncSetAttribute(alpha_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr[ctx->device & 15][from_inverse] = true;
+  }
+  const long long fs = (long long)Np * Np, ds = (long long)gp->NB * NBK * NBK;
+  if (from_inverse) alpha_kernel<true><<<count, ALPHA_THREADS, smem, ctx->stream>>>(gp->fac, fs, Np, gp->dinvT, ds, gp->beta, gp->alpha, s0);
+  else alpha_kernel<false><<<count, ALPHA_THREADS, smem, ctx->stream>>>(gp->fac, fs, Np, gp->dinvT, ds, gp->beta, gp->alpha, s0);
+  b7_count(ctx);
   B7_CUDA(cudaGetLastError());
   return 0;
 }

@@ -26,12 +26,13 @@ typedef struct b7_ctx b7_ctx;
 typedef struct b7_grid b7_grid;
 typedef struct b7_gp b7_gp;
 typedef struct b7_blr b7_blr;
+typedef struct b7_comm b7_comm;
 
 enum { B7_KERNEL_ARDSE = 0, B7_KERNEL_MATERN52 = 1 };           /* bots/bayesopt.lua:41 model.kernel */
 enum { B7_SCORE_EI = 0, B7_SCORE_CB = 1 };                       /* scores/init.lua */
 enum { B7_BOUND_LOWER = 0, B7_BOUND_UPPER = 1 };                 /* scores/confidence_bound.lua:32 */
 enum { B7_FIT_PREDICT = 0, B7_FIT_LOGML_ONLY = 1, B7_FIT_DEFER = 2 }; /* flags of b7_gp_fit */
-enum { B7_ERR_ARG = -1, B7_ERR_CUDA = -2, B7_ERR_STATE = -3, B7_ERR_NOMEM = -4 };
+enum { B7_ERR_ARG = -1, B7_ERR_CUDA = -2, B7_ERR_STATE = -3, B7_ERR_NOMEM = -4, B7_ERR_NCCL = -5 };
 
 int         b7_version(void);
 const char* b7_last_error(void);
@@ -158,6 +159,49 @@ int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int 
                  double fmin, double* score_host, int64_t* argmax, int64_t* argmax_original,
                  double* best, int64_t* nan_count);
 void b7_blr_free(b7_blr* blr);
+
+/* ---- multi-GPU: candidate shards + draw-sharded fit (bots/bayesopt.lua:56-99 over config.bot.nGPU devices) ----
+ * The path shards by candidates: rank g of G scores the contiguous original-row range
+ * [g*floor(M/G) + min(g, M%G), ...) of the grid; the S factorisations are split the same way over the ranks and
+ * exchanged once per fit with NCCL over NVLink (in the form the posterior pass reads: the packed int8 slices of
+ * L^-1 + row scales + alpha on the INT8 path, L^-1 + beta on the FP64 path); the per-rank (best, index, nan)
+ * triples are all-gathered and combined with "larger score, then smaller original index" -- the reference's
+ * first-maximum scan for any G.  libnccl.so.2 is loaded at run time (dlopen) by the first b7_comm_* call.
+ *
+ * A communicator drives n_local devices of this process out of `world` ranks:
+ *   b7_comm_init_all   one process, all listed devices (what the LuaJIT host calls): world = n_local = n_gpus;
+ *   b7_comm_init_rank  one process per GPU (torchrun): rank 0 calls b7_comm_unique_id, the 128 bytes travel by any
+ *                      means (torch.distributed, a file), every rank calls b7_comm_init_rank. */
+int  b7_comm_init_all(int n_gpus, const int* device_ids /* nullable: 0 .. n_gpus-1 */, b7_comm** out);
+int  b7_comm_unique_id(char* id128);
+int  b7_comm_init_rank(int device, const char* id128, int world, int rank, b7_comm** out);
+int  b7_comm_world(b7_comm* comm);
+int  b7_comm_local_count(b7_comm* comm);
+int  b7_comm_first_rank(b7_comm* comm);
+b7_ctx* b7_comm_ctx(b7_comm* comm, int local_index);
+void b7_comm_free(b7_comm* comm);
+/* rows [row0, row0 + count) of M rows owned by `rank` of `world` (the same rule shards the S draws of a fit) */
+int  b7_shard_range(int64_t M, int world, int rank, int64_t* row0, int64_t* count);
+/* Sobol grid of `count` points from first_seed, each local device generating only its own shard;
+ * out_grids: n_local handles (free each with b7_grid_free).  Indices reported for them are global. */
+int  b7_sobol_generate_sharded(b7_comm* comm, int dims, int64_t first_seed, int64_t count, const double* mins,
+                               const double* maxes, b7_grid** out_grids);
+/* any host grid (grids/random.lua or cached candidates): X is the full M x d matrix on every process */
+int  b7_grid_from_host_sharded(b7_comm* comm, const double* X, int64_t M, int d, b7_grid** out_grids);
+/* utils.tensor.steal on the sharded grid: `compacted_index` is global (1-based, current compacted numbering);
+ * every process makes the same call */
+int  b7_grid_remove_sharded(b7_comm* comm, b7_grid** grids, int64_t compacted_index, double* removed_row /* nullable, d */);
+/* b7_gp_fit over the communicator: every rank factorises and inverts its share of the S draws, one NCCL
+ * all-gather fills the rest.  out_gps: n_local handles, each holding all S draws; info / logml / jitter: S entries.
+ * gather_ms (nullable): device time of the exchange on the first local device. */
+int  b7_gp_fit_sharded(b7_comm* comm, int kernel, const double* X, const double* y, int N, int d, const double* hyp, int S,
+                       int H, int noiseless, b7_gp** out_gps, int* info, double* logml, double* jitter, double* gather_ms);
+/* b7_acq_score over the communicator: each local device scores its shard with all S factors, then the triples are
+ * combined.  score_host (nullable): the scores of the local shards, concatenated in local-device order (the whole
+ * grid with b7_comm_init_all); argmax / argmax_original are global 1-based indices (compacted / original). */
+int  b7_acq_score_multi(b7_comm* comm, b7_gp** gps, b7_grid** grids, int kind, double tradeoff, int bound, double sign,
+                        double fmin, double* score_host, int64_t* argmax, int64_t* argmax_original, double* best,
+                        int64_t* nan_count);
 
 #ifdef __cplusplus
 }

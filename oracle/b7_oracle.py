@@ -21,9 +21,13 @@ uses (dpotrf / dtrtrs / dgemm).
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import scipy.linalg as sla
+
+THREADS = int(os.environ.get("B7_ORACLE_THREADS", os.cpu_count() or 1))   # element loops; BLAS has its own pool
 
 # --------------------------------------------------------------------------------------------
 # Sobol (PINNED: grids/sobol.lua, utils/bits.lua)
@@ -387,22 +391,53 @@ def parse_hyp(hyp, d):
     return w, sf2, sn2, float(hyp[d + 2])
 
 
-def cov(kernel, A, B, w, sf2):
-    """DECLARED. r2 = sum_d ((a_d - b_d) * w_d)^2, accumulated in d order.
-    ARD-SE: sf2*exp(-r2/2); Matern-5/2: sf2*(1 + sqrt5 r + 5 r2/3) exp(-sqrt5 r)."""
-    A = np.asarray(A, dtype=np.float64)
-    B = np.asarray(B, dtype=np.float64)
+def _cov_block(kernel, A, B, w, sf2, out):
+    """One block of the covariance (rows of A x all of B) written into `out`; the per-element operation
+    order is the declared one: r2 accumulated in dimension order, every operation rounded separately."""
     r2 = np.zeros((A.shape[0], B.shape[0]))
+    t = np.empty_like(r2)
     for k in range(A.shape[1]):
-        t = (A[:, k][:, None] - B[:, k][None, :]) * w[k]
-        r2 += t * t
+        np.subtract(A[:, k][:, None], B[:, k][None, :], out=t)
+        np.multiply(t, w[k], out=t)
+        np.multiply(t, t, out=t)
+        r2 += t
     if kernel == KERNEL_ARDSE:
-        return sf2 * np.exp(-0.5 * r2)
+        np.multiply(r2, -0.5, out=r2)
+        np.exp(r2, out=r2)
+        np.multiply(r2, sf2, out=out)
+        return out
     if kernel == KERNEL_MATERN52:
         r = np.sqrt(r2)
         s5r = math.sqrt(5.0) * r
-        return sf2 * ((1.0 + s5r + (5.0 / 3.0) * r2) * np.exp(-s5r))
+        np.multiply(sf2, (1.0 + s5r + (5.0 / 3.0) * r2) * np.exp(-s5r), out=out)
+        return out
     raise ValueError(kernel)
+
+
+_COV_BLOCK_ENTRIES = 1 << 18     # block of ~2 MB per temporary: stays in a core's L2
+
+
+def cov(kernel, A, B, w, sf2):
+    """DECLARED. r2 = sum_d ((a_d - b_d) * w_d)^2, accumulated in d order.
+    ARD-SE: sf2*exp(-r2/2); Matern-5/2: sf2*(1 + sqrt5 r + 5 r2/3) exp(-sqrt5 r).
+
+    Evaluated in one blocked pass (row blocks of A sized for the cache, spread over the host threads like
+    TH's OpenMP element loops) instead of d full M x N temporaries; every entry sees the same operations in
+    the same order, so the values do not depend on the blocking."""
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    if kernel not in (KERNEL_ARDSE, KERNEL_MATERN52):
+        raise ValueError(kernel)
+    out = np.empty((A.shape[0], B.shape[0]))
+    rows = max(1, _COV_BLOCK_ENTRIES // max(B.shape[0], 1))
+    starts = range(0, A.shape[0], rows)
+    if len(starts) <= 1 or THREADS <= 1:
+        for r0 in starts:
+            _cov_block(kernel, A[r0:r0 + rows], B, w, sf2, out[r0:r0 + rows])
+        return out
+    with ThreadPoolExecutor(THREADS) as ex:
+        list(ex.map(lambda r0: _cov_block(kernel, A[r0:r0 + rows], B, w, sf2, out[r0:r0 + rows]), starts))
+    return out
 
 
 def gp_fit(X, y, hyp, kernel=KERNEL_ARDSE, noiseless=False):
@@ -423,12 +458,18 @@ def gp_fit(X, y, hyp, kernel=KERNEL_ARDSE, noiseless=False):
                 jitter=jit, iters=iters, logml=logml)
 
 
-def gp_predict(fit, Xs, include_noise=False):
-    """DECLARED. mean = m + k*^T alpha; var = max(sf2 - colsumsq(L^-1 k*), 0) (+ sn2 on request)."""
-    Ks = cov(fit["kernel"], np.asarray(Xs, dtype=np.float64), fit["X"], fit["w"], fit["sf2"])  # M x N
-    mean = fit["m"] + Ks @ fit["alpha"]
-    V = sla.solve_triangular(fit["L"], Ks.T, lower=True)
-    var = fit["sf2"] - np.einsum("ij,ij->j", V, V)
+def gp_predict(fit, Xs, include_noise=False, chunk=8192):
+    """DECLARED. mean = m + k*^T alpha; var = max(sf2 - colsumsq(L^-1 k*), 0) (+ sn2 on request).
+    Candidates are processed in chunks so that K* and V (chunk x N) stay small; per candidate the arithmetic is
+    the same for any chunk size up to BLAS's own blocking."""
+    Xs = np.asarray(Xs, dtype=np.float64)
+    M = Xs.shape[0]
+    mean, var = np.empty(M), np.empty(M)
+    for c0 in range(0, max(M, 1), chunk):
+        Ks = cov(fit["kernel"], Xs[c0:c0 + chunk], fit["X"], fit["w"], fit["sf2"])  # chunk x N
+        mean[c0:c0 + chunk] = fit["m"] + Ks @ fit["alpha"]
+        V = sla.solve_triangular(fit["L"], Ks.T, lower=True)
+        var[c0:c0 + chunk] = fit["sf2"] - np.einsum("ij,ij->j", V, V)
     var = np.maximum(var, 0.0)
     if include_noise:
         var = var + fit["sn2"]

@@ -401,16 +401,40 @@ def test_more_than_16384_observations_stay_on_the_fp64_kernels(ctx, oracle):
     f.free()
 
 
+def refined_alpha(oracle, fit, y):
+    """alpha = K_y^-1 (y - m) with two steps of iterative refinement whose residual is formed in extended precision
+    (numpy longdouble, 64-bit mantissa) from the fp64 entries of K_y: an estimate of the exact solution of the
+    system the fp64 algorithms solve, good to ~cond * 2^-64.  Test infrastructure (used to measure the oracle's own
+    error where cond(K) * eps exceeds the 1e-9 bar)."""
+    import scipy.linalg as sla
+    X, L_ = fit["X"], fit["L"]
+    K = oracle.cov(fit["kernel"], X, X, fit["w"], fit["sf2"])
+    K[np.diag_indices(K.shape[0])] += fit["sn2"] + fit["jitter"]
+    r = (y - fit["m"]).astype(np.longdouble)
+    alpha = fit["alpha"].astype(np.longdouble)
+    for _ in range(2):
+        res = r.copy()
+        for c0 in range(0, K.shape[0], 2048):                      # K in longdouble, 2048 rows at a time
+            res[c0:c0 + 2048] -= K[c0:c0 + 2048].astype(np.longdouble) @ alpha
+        dz = sla.solve_triangular(L_.T, sla.solve_triangular(L_, res.astype(np.float64), lower=True), lower=False)
+        alpha = alpha + dz.astype(np.longdouble)
+    return alpha
+
+
 def test_int8_path_at_its_largest_size_matches_the_fp64_path(ctx, oracle):
     # N = 16384: the longest int32 accumulations the INT8 kernels are allowed to run (posterior k = 16384, inversion
-    # k = 8192); inverse and posterior against the all-FP64 path on the same problem
-    N, d = 16384, 3
+    # k = 8192); inverse and posterior of both paths against the oracle on 2048 candidates.
+    # Bars: variance 1e-9 sf2 (north_star).  Mean: cond(K) ~ N sf2 / sn2 = 2e6 and |alpha| ~ 1e2, so two correct fp64
+    # algorithms differ by ~cond * eps * |alpha| ~ 1e-8 -- the 1e-9 bar is below what fp64 can resolve for this system.
+    # The test therefore measures the oracle's own error against an extended-precision refinement of alpha and holds
+    # the GPU paths to the same reference: GPU error <= max(1e-9, 3 x the LAPACK oracle's error).
+    N, d, M = 16384, 3, 2048
     r = np.random.default_rng(3)
     X = oracle.sobol_points(d, N)
     y = oracle.ackley(X)
     y = (y - y.mean()) / y.std()
     hyp = np.array([[np.log(0.2), np.log(0.3), np.log(0.25), 0.1, 0.5 * np.log(1e-2), 0.05]])
-    Xc = r.random((500, d))
+    Xc = r.random((M, d))
     keep = ctx.posterior_path()
     out = {}
     try:
@@ -425,15 +449,28 @@ def test_int8_path_at_its_largest_size_matches_the_fp64_path(ctx, oracle):
     a, b = out[L.PATH_FP64_DMMA], out[L.PATH_INT8_OZAKI]
     sf2 = np.exp(2 * hyp[0, 3])
     assert a[0] == b[0]                                               # single factor: the same FP64 factorisation
-    # cond(K) ~ N sf2 / sn2 = 2e6 and |alpha| ~ 1e2: any two fp64 algorithms differ by ~1e-8 in the mean here
     dm, dv = np.max(np.abs(a[1] - b[1])), np.max(np.abs(a[2] - b[2])) / sf2
-    print("N = 16384, int8 vs fp64 path: max |mean diff| %.2e, max |var diff| / sf2 %.2e" % (dm, dv))
     assert dm <= 5e-8 and dv <= 1e-9
     assert np.all(b[2] >= 0) and np.all(b[2] <= sf2 * (1 + 1e-12))
     ref = oracle.gp_fit(X, y, hyp[0], 0)
-    m_ref, v_ref = oracle.gp_predict(ref, Xc[:40])
-    for mv in (a, b):
-        assert np.max(np.abs(mv[1][:40] - m_ref)) <= 1e-7 and np.max(np.abs(mv[2][:40] - v_ref)) <= 1e-8 * sf2
+    m_ref, v_ref = oracle.gp_predict(ref, Xc)
+    alpha_x = refined_alpha(oracle, ref, y)
+    Ks = oracle.cov(0, Xc, X, ref["w"], ref["sf2"])
+    m_x = (ref["m"] + Ks.astype(np.longdouble) @ alpha_x).astype(np.float64)
+    oracle_err = float(np.max(np.abs(m_ref - m_x)))
+    report = {"N": N, "candidates": M, "cond_estimate": N * sf2 / 1e-2, "oracle_mean_vs_extended_precision": oracle_err,
+              "paths_mean_diff": float(dm), "paths_var_diff_over_sf2": float(dv)}
+    for name, mv in (("fp64_dmma", a), ("int8_ozaki", b)):
+        e = posterior_errors(mv[1], mv[2], m_ref, v_ref, sf2)
+        e["mean_vs_extended_precision"] = float(np.max(np.abs(mv[1] - m_x)))
+        report[name] = e
+    record_parity("largest_int8_N16384", report)
+    print("N = 16384:", report)
+    for name in ("fp64_dmma", "int8_ozaki"):
+        e = report[name]
+        assert e["var_over_sf2"] <= 1e-9, report                                          # north_star bar
+        assert e["mean_vs_extended_precision"] <= max(1e-9, 3 * oracle_err), report       # see the comment above
+        assert e["mean"] <= max(1e-9, 4 * oracle_err), report
 
 
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
@@ -529,6 +566,131 @@ def test_posterior_properties_large(ctx, oracle):
     mu, var = f.predict(0, Xc[:2000])
     assert rel(mu, mr, 1.0) <= 1e-9 and rel(var, vr, fit["sf2"]) <= 1e-9
     f.free()
+
+
+def record_parity(key, values):
+    """Measured maxima of the headline-size parity tests -> gpurun_out/parity_r02.json (copied to profiles/)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "parity_r02.json")
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[key] = values
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+
+
+def posterior_errors(mu, var, mu_ref, var_ref, sf2):
+    """The four figures every size-parity test reports: mean (against max(|mean|, 1)), variance against the prior
+    variance, variance strictly relative where var >= 1e-3 sf2, and the smallest variance seen."""
+    big = var_ref >= 1e-3 * sf2
+    return {"mean": rel(mu, mu_ref, 1.0), "var_over_sf2": float(np.max(np.abs(var - var_ref)) / sf2),
+            "var_rel_where_ge_1e-3_sf2": float(np.max(np.abs(var - var_ref)[big] / var_ref[big])) if big.any() else 0.0,
+            "frac_var_ge_1e-3_sf2": float(np.mean(big)), "min_var_over_sf2": float(var_ref.min() / sf2)}
+
+
+def test_headline_config_both_paths_against_the_oracle(ctx, oracle):
+    """The shape BASELINE.json's metric is quoted on and bench.py times -- N = 4096, d = 6, sigma_n^2 = 1e-2, bench.py's own
+    hyper_draws() and Sobol grid -- against oracle.acquisition, on both posterior paths.  4 of the 32 draws (the rows with
+    the shortest and the longest length-scales and two more), 2 posterior panels = 37 888 candidates.
+    Call sites matched: scores/expected_improvement.lua:63-66 (predict + fmin), bots/bayesopt.lua:73-79,96 (average, argmax).
+    Bars (north_star): mean 1e-9, variance 1e-9 sf2 and 1e-9 relative where var >= 1e-3 sf2, EI 1e-7, argmax identical."""
+    import bench
+    N, d, M = bench.N_OBS, bench.DIMS, bench.M_STEP
+    pts = grids.sobol({"size": N + M, "dims": d})()
+    assert np.array_equal(pts, oracle.sobol_points(d, N + M))
+    Xo, Xc = pts[:N], pts[N:]
+    y = bench.hartmann6(Xo)
+    assert np.allclose(y, oracle.hartmann6(Xo), rtol=1e-14, atol=0)
+    y = (y - y.mean()) / y.std()
+    hyp32 = bench.hyper_draws(bench.S_DRAWS, d)
+    ls = hyp32[:, :d].sum(1)
+    rows = [int(np.argmin(ls)), int(np.argmax(ls))]
+    rows = sorted(rows + [s for s in range(bench.S_DRAWS) if s not in rows][:2])
+    assert len(set(rows)) == 4
+    hyp = hyp32[rows]
+    ref = oracle.acquisition(Xo, y, hyp, Xc, 0, False, oracle.SCORE_EI)
+    keep = ctx.posterior_path()
+    report = {"N": N, "d": d, "candidates": M, "draw_rows": rows, "sigma_n2": 1e-2}
+    try:
+        for path, name in ((L.PATH_INT8_OZAKI, "int8_ozaki"), (L.PATH_FP64_DMMA, "fp64_dmma")):
+            ctx.set_posterior_path(path)
+            f = models.GPFactors(Xo, y, hyp)
+            assert (f.info == 0).all() and (f.jitter == 0).all()
+            worst = {}
+            for s in range(len(rows)):
+                sf2 = np.exp(2 * hyp[s, d])
+                mu, var = f.predict(s, Xc)
+                e = posterior_errors(mu, var, ref["mean"][s], ref["var"][s], sf2)
+                worst = {k: (max(worst.get(k, 0.0), v) if k != "min_var_over_sf2" else min(worst.get(k, 1.0), v)) for k, v in e.items()}
+            grid = grids.DeviceGrid.from_host(Xc)
+            sc = np.empty(M)
+            am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+            L.check(L.lib().b7_acq_score(f.handle, grid.handle, L.SCORE_EI, 0.0, 0, -1.0, float(y.min()), L.dptr(sc), C.byref(am),
+                                         C.byref(amo), C.byref(best), C.byref(nn)))
+            worst["ei_rel"] = rel(sc, ref["score"], 1e-6 * ref["score"].max())
+            worst["logml_rel"] = rel(f.logml, np.array([oracle.gp_fit(Xo, y, h, 0)["logml"] for h in hyp]), 1e-300)
+            worst["argmax"] = int(am.value)
+            worst["argmax_oracle"] = int(ref["idx"])
+            report[name] = worst
+            record_parity("headline_N4096", report)
+            assert worst["mean"] <= 1e-9, worst                           # north_star: mean 1e-9
+            assert worst["var_over_sf2"] <= 1e-9, worst                   # variance 1e-9 of the prior variance
+            assert worst["var_rel_where_ge_1e-3_sf2"] <= 1e-9, worst      # and 1e-9 strictly relative down to 1e-3 sf2
+            assert worst["ei_rel"] <= 1e-7, worst                         # EI 1e-7
+            assert am.value == ref["idx"] == amo.value and nn.value == 0  # selected candidate: identical
+            assert worst["logml_rel"] <= 1e-11
+            grid.free()
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
+
+
+def test_headline_noiseless_variant_reports_scaled_error(ctx, oracle):
+    """Noiseless variant (diag = 1e-6 + 1e-8 sf2, cond(K) ~ 1e9) at N = 2048 with bench.py's draws: two correct fp64
+    algorithms differ by cond * eps here (LAPACK against an extended-precision solve differs by ~3e-9 relative, DESIGN.md
+    section 2), so the bar is the scaled one: variance 1e-9 of the prior variance, mean 1e-6 absolute; argmax identical
+    or a tie within 1e-9 relative."""
+    import bench
+    N, d, M = 2048, 6, 18944
+    pts = grids.sobol({"size": N + M, "dims": d})()
+    Xo, Xc = pts[:N], pts[N:]
+    y = bench.hartmann6(Xo)
+    y = (y - y.mean()) / y.std()
+    hyp = bench.hyper_draws(bench.S_DRAWS, d)[[3, 11]]
+    hyp[:, d + 1] = 0.5 * np.log(1e-6)
+    ref = oracle.acquisition(Xo, y, hyp, Xc, 0, True, oracle.SCORE_EI)
+    keep = ctx.posterior_path()
+    report = {"N": N, "candidates": M, "sigma_n2": 1e-6, "noiseless": True}
+    try:
+        for path, name in ((L.PATH_INT8_OZAKI, "int8_ozaki"), (L.PATH_FP64_DMMA, "fp64_dmma")):
+            ctx.set_posterior_path(path)
+            f = models.GPFactors(Xo, y, hyp, "ardse", noiseless=True)
+            assert (f.info == 0).all()
+            worst = {}
+            for s in range(2):
+                mu, var = f.predict(s, Xc)
+                e = posterior_errors(mu, var, ref["mean"][s], ref["var"][s], np.exp(2 * hyp[s, d]))
+                worst = {k: (max(worst.get(k, 0.0), v) if k != "min_var_over_sf2" else min(worst.get(k, 1.0), v)) for k, v in e.items()}
+            grid = grids.DeviceGrid.from_host(Xc)
+            sc = np.empty(M)
+            am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+            L.check(L.lib().b7_acq_score(f.handle, grid.handle, L.SCORE_EI, 0.0, 0, -1.0, float(y.min()), L.dptr(sc), C.byref(am),
+                                         C.byref(amo), C.byref(best), C.byref(nn)))
+            worst["ei_abs_over_max"] = float(np.max(np.abs(sc - ref["score"])) / ref["score"].max())
+            worst["argmax"], worst["argmax_oracle"] = int(am.value), int(ref["idx"])
+            report[name] = worst
+            record_parity("noiseless_N2048", report)
+            assert worst["var_over_sf2"] <= 1e-9 and worst["mean"] <= 1e-6, worst
+            if am.value != ref["idx"]:
+                gap = abs(ref["score"][am.value - 1] - ref["best"]) / abs(ref["best"])
+                assert gap <= 1e-9, f"argmax differs beyond a near-tie: {am.value} vs {ref['idx']} (gap {gap})"
+            grid.free()
+            f.free()
+    finally:
+        ctx.set_posterior_path(keep)
 
 
 def test_sharded_acquisition_equals_single(ctx, oracle):
