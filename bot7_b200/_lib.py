@@ -73,6 +73,20 @@ SIGNATURES = {
     "b7_blr_predict": (_i, [_p, _i, _dp, _l, _dp, _dp]),
     "b7_blr_score": (_i, [_p, _p, _i, _d, _i, _d, _d, _dp, _lp, _lp, _dp, _lp]),
     "b7_blr_free": (None, [_p]),
+    "b7_comm_init_all": (_i, [_i, _ip, C.POINTER(_p)]),
+    "b7_comm_unique_id": (_i, [C.c_char_p]),
+    "b7_comm_init_rank": (_i, [_i, C.c_char_p, _i, _i, C.POINTER(_p)]),
+    "b7_comm_world": (_i, [_p]),
+    "b7_comm_local_count": (_i, [_p]),
+    "b7_comm_first_rank": (_i, [_p]),
+    "b7_comm_ctx": (_p, [_p, _i]),
+    "b7_comm_free": (None, [_p]),
+    "b7_shard_range": (_i, [_l, _i, _i, _lp, _lp]),
+    "b7_sobol_generate_sharded": (_i, [_p, _i, _l, _l, _dp, _dp, C.POINTER(_p)]),
+    "b7_grid_from_host_sharded": (_i, [_p, _dp, _l, _i, C.POINTER(_p)]),
+    "b7_grid_remove_sharded": (_i, [_p, C.POINTER(_p), _l, _dp]),
+    "b7_gp_fit_sharded": (_i, [_p, _i, _dp, _dp, _i, _i, _dp, _i, _i, _i, C.POINTER(_p), _ip, _dp, _dp, _dp]),
+    "b7_acq_score_multi": (_i, [_p, C.POINTER(_p), C.POINTER(_p), _i, _d, _i, _d, _d, _dp, _lp, _lp, _dp, _lp]),
 }
 
 

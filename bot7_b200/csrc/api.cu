@@ -219,6 +219,11 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evA, cudaEventDisableTiming));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evB, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    B7_CUDA(cudaEventCreateWithFlags(&ctx->evK[i], cudaEventDisableTiming));
+    B7_CUDA(cudaEventCreateWithFlags(&ctx->evP[i], cudaEventDisableTiming));
+  }
+  { const char* e = getenv("B7_KSTAR_OVERLAP"); ctx->kstar_overlap = !(e && e[0] == '0'); }
   cudaMemPool_t pool;
   B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
@@ -250,6 +255,7 @@ void b7_shutdown(b7_ctx* ctx) {
   { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->evK[i]); cudaEventDestroy(ctx->evP[i]); }
   cudaStreamDestroy(ctx->stream2);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -416,7 +422,7 @@ void b7_gp_free(b7_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->ctx->device);
   cudaStreamSynchronize(gp->ctx->stream);
-  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->alpha, gp->tt, gp->logdet, gp->info};
+  void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->alpha, gp->tt, gp->logdet, gp->info, gp->meta_dev};
   for (void* p : ptrs) dev_free(gp->ctx, p);
   delete gp;
 }
@@ -580,6 +586,49 @@ int b7_gp_mark_ready(b7_gp* gp) {
   return 0;
 }
 
+}  // extern "C"
+
+// sharded fit: own draws [s0, s0 + count) are factorised and inverted; make sure every buffer of the exchange exists
+// and publish (info, log ml, jitter) of the own draws in device memory
+int b7_gp_prepare_gather(b7_gp* gp, int s0, int count) {
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  if (i8_path(gp) && !gp->facS) {
+    B7_CHECK(dev_alloc(ctx, &gp->facS, (size_t)gp->S * b7_i8_facs_stride(gp->Np)));
+    B7_CHECK(dev_alloc(ctx, &gp->sigma, (size_t)gp->S * gp->Np));
+  }
+  if (!gp->meta_dev) B7_CHECK(dev_alloc(ctx, &gp->meta_dev, (size_t)gp->S * 3));
+  std::vector<double> m((size_t)std::max(count, 1) * 3);
+  for (int i = 0; i < count; ++i) {
+    m[3 * i] = (double)gp->info_host[s0 + i];
+    m[3 * i + 1] = gp->logml_host[s0 + i];
+    m[3 * i + 2] = gp->jitter[s0 + i];
+  }
+  if (count > 0) B7_CUDA(cudaMemcpyAsync(gp->meta_dev + 3 * (size_t)s0, m.data(), (size_t)count * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b7_gp_finish_gather(b7_gp* gp, bool slices_exchanged) {
+  b7_ctx* ctx = gp->ctx;
+  B7_CUDA(cudaSetDevice(ctx->device));
+  std::vector<double> m((size_t)gp->S * 3);
+  B7_CUDA(cudaMemcpyAsync(m.data(), gp->meta_dev, m.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B7_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < gp->S; ++s) {
+    gp->info_host[s] = (int)m[3 * s];
+    gp->logml_host[s] = m[3 * s + 1];
+    gp->jitter[s] = m[3 * s + 2];
+  }
+  std::fill(gp->sliced.begin(), gp->sliced.end(), slices_exchanged ? 1 : 0);
+  gp->fac_complete = !slices_exchanged;
+  gp->ready = true;
+  gp->inverted = true;
+  return 0;
+}
+
+extern "C" {
+
 int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, int d, const double* hyp, int S,
               int H, int noiseless, int flags, b7_gp** out, int* info, double* logml, double* jitter) {
   if (!ctx || !out) { b7_set_error("gp_fit: null ctx/out"); return B7_ERR_ARG; }
@@ -696,6 +745,10 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
   const int64_t rp = pad128(rows);
   B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, (size_t)rp * gp->Np * 8));
   const double* p = gp->par_host.data() + (size_t)s * kParStride;
+  if (!gp->fac_complete && (!i8_path(gp) || !gp->sliced[s])) {
+    b7_set_error("gp: this handle came from a sharded fit that exchanged the int8 slices only; refit to use the FP64 path");
+    return B7_ERR_STATE;
+  }
   if (i8_path(gp)) {
     if (!gp->sliced[s]) B7_CHECK(gp_slice(gp, s, 1));     // the path was switched after the fit
     // error-free sliced operands on the INT8 tensor pipe (posterior_i8.cu); K* needs no max: 0 < k* <= sf2 <= tau
@@ -731,6 +784,57 @@ static int posterior_panel(b7_gp* gp, int s, const double* A, int64_t rows, doub
     t.stop(1);
   }
   return 0;
+}
+
+// All S draws of one candidate panel on the INT8 path with the K* pass of draw s + 1 (FP64 / integer pipes, second
+// stream) running under the posterior pass of draw s (tensor pipe, main stream): two sets of K* slices and partials.
+// Used when stage profiling is off (the stage timers need the two passes one after the other).
+static int posterior_panel_draws_i8(b7_gp* gp, const double* A, int64_t rows, double* dm, double* dv, int64_t ld) {
+  b7_ctx* ctx = gp->ctx;
+  const int S = gp->S;
+  const int64_t rp64 = (rows + 63) / 64 * 64;
+  const size_t ks_bytes = ((size_t)rp64 * gp->Np * B7_I8_SLICES + 255) / 256 * 256;
+  const size_t part_bytes = (b7_i8_partial_bytes(gp->Np, rp64) + 255) / 256 * 256;
+  B7_CHECK(grow(ctx, &ctx->ks, &ctx->ks_bytes, 2 * ks_bytes));
+  B7_CHECK(grow(ctx, &ctx->i8_partial, &ctx->i8_partial_bytes, 2 * part_bytes));
+  for (int s = 0; s < S; ++s)
+    if (!gp->sliced[s]) B7_CHECK(gp_slice(gp, s, 1));
+  auto tau_of = [&](int s) {
+    int e = 0;
+    frexp(gp->par_host[(size_t)s * kParStride + B7_MAX_DIMS], &e);
+    return ldexp(1.0, e);
+  };
+  auto ks_of = [&](int s) { return reinterpret_cast<int8_t*>(ctx->ks) + (size_t)(s & 1) * ks_bytes; };
+  auto part_of = [&](int s) { return reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->i8_partial) + (size_t)(s & 1) * part_bytes); };
+  auto kstar = [&](int s) {
+    return b7_i8_cov_slices(ctx, ctx->stream2, gp->kernel, A, rows, rp64, gp->d, gp->Xt, gp->N, gp->Np, gp->par + (size_t)s * kParStride, tau_of(s),
+                            gp->alpha + (size_t)s * gp->Np, ks_of(s), b7_i8_mean_partials(part_of(s), gp->Np, rp64));
+  };
+  // the second stream starts after everything already queued on the main one (the grid, the factors)
+  B7_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
+  B7_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->evA, 0));
+  B7_CHECK(kstar(0));
+  B7_CUDA(cudaEventRecord(ctx->evK[0], ctx->stream2));
+  for (int s = 0; s < S; ++s) {
+    if (s + 1 < S) {
+      if (s >= 1) B7_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->evP[(s + 1) & 1], 0));   // posterior s - 1 has released that set
+      B7_CHECK(kstar(s + 1));
+      B7_CUDA(cudaEventRecord(ctx->evK[(s + 1) & 1], ctx->stream2));
+    }
+    B7_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evK[s & 1], 0));
+    const double* p = gp->par_host.data() + (size_t)s * kParStride;
+    B7_CHECK(b7_launch_posterior_i8(ctx, gp->facS + (size_t)s * b7_i8_facs_stride(gp->Np), gp->sigma + (size_t)s * gp->Np, gp->Np, ks_of(s), A, rows,
+                                    gp->d, gp->Xt, gp->par + (size_t)s * kParStride, gp->kernel, rp64, tau_of(s), p[B7_MAX_DIMS], p[B7_MAX_DIMS + 2],
+                                    part_of(s), dm + (size_t)s * ld, dv + (size_t)s * ld));
+    B7_CUDA(cudaEventRecord(ctx->evP[s & 1], ctx->stream));
+  }
+  return 0;
+}
+
+static bool all_sliced_or_sliceable(const b7_gp* gp) {
+  if (gp->fac_complete) return true;
+  for (char c : gp->sliced) if (!c) return false;
+  return true;
 }
 
 static int require_predict_state(b7_gp* gp) {
@@ -797,6 +901,7 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
     b7_set_error("acq_score: bad arguments (grid dims %d vs model dims %d)", grid ? grid->d : -1, gp ? gp->d : -1);
     return B7_ERR_ARG;
   }
+  if (grid->ctx != gp->ctx) { b7_set_error("acq_score: the grid and the model live on different contexts / devices"); return B7_ERR_ARG; }
   B7_CHECK(require_predict_state(gp));
   b7_ctx* ctx = gp->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
@@ -808,16 +913,18 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
   PartBuf pb(ctx);
   pb.cap = (int)(n_panels * b7_score_grid_size(ctx, P)) + 1;
   B7_CHECK(dev_alloc(ctx, &pb.best, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.idx, (size_t)pb.cap)); B7_CHECK(dev_alloc(ctx, &pb.nan, (size_t)pb.cap));
-  double* score_dev = nullptr;
-  if (score_host) B7_CHECK(dev_alloc(ctx, &score_dev, (size_t)std::max<int64_t>(count, 1)));
+  struct ScoreBuf { b7_ctx* c; double* p; ~ScoreBuf() { dev_free(c, p); } } sb{ctx, nullptr};
+  if (score_host) B7_CHECK(dev_alloc(ctx, &sb.p, (size_t)std::max<int64_t>(count, 1)));
+  double* const score_dev = sb.p;
   int n_parts = 0, rc = 0;
   for (int64_t c0 = 0; c0 < count && rc == 0; c0 += P) {
     const int64_t n = std::min(P, count - c0), np = pad128(n);
     double* dm = ctx->moments; double* dv = ctx->moments + (size_t)S * np;
-    // (running the K* pass of draw s + 1 on a second stream under the posterior pass of draw s was tried: no gain,
-    // the power cap hands the time back)
-    for (int s = 0; s < S && rc == 0; ++s)
-      rc = posterior_panel(gp, s, grid->X + (row0 + c0) * grid->d, n, dm + (size_t)s * np, dv + (size_t)s * np);
+    if (i8_path(gp) && ctx->kstar_overlap && !ctx->profiling && S > 1 && all_sliced_or_sliceable(gp))
+      rc = posterior_panel_draws_i8(gp, grid->X + (row0 + c0) * grid->d, n, dm, dv, np);
+    else
+      for (int s = 0; s < S && rc == 0; ++s)
+        rc = posterior_panel(gp, s, grid->X + (row0 + c0) * grid->d, n, dm + (size_t)s * np, dv + (size_t)s * np);
     if (rc < 0) break;
     StageTimer t(ctx, ST_SCORE);
     int parts = 0;
@@ -834,7 +941,6 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { b7_set_error("acq_score D2H: %s", cudaGetErrorString(e)); rc = B7_ERR_CUDA; }
   }
-  dev_free(ctx, score_dev);
   if (rc < 0) return rc;
   if (argmax_original) *argmax_original = r0 + 1;
   if (best) *best = bv;

@@ -37,6 +37,8 @@ struct b7_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;                 // far trailing updates of the Cholesky (overlaps the next panel)
   cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t evK[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};   // K* pass of draw s + 1 under the posterior pass of draw s
+  bool kstar_overlap = true;     // B7_KSTAR_OVERLAP=0: K* and posterior strictly one after the other
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   double stage_ms[ST_COUNT] = {0};
   int64_t stage_calls[ST_COUNT] = {0};
@@ -73,6 +75,10 @@ struct b7_grid {
   int64_t* removed_dev = nullptr; // device copy (capacity grows)
   int64_t removed_cap = 0;
   bool removed_dirty = false;
+  // sharded grids (multi.cu): this handle holds rows [row_base, row_base + rows) of a grid of rows_total rows;
+  // removed_global is the tombstone list of the whole grid (global original rows, sorted), replicated on every shard
+  int64_t row_base = 0, rows_total = 0;
+  std::vector<int64_t> removed_global;
 };
 
 struct b7_gp {
@@ -95,6 +101,8 @@ struct b7_gp {
   double* tt = nullptr;     // device S x (128 x Np tiled) : scratch of the inversion sweep
   double* logdet = nullptr; // device S : sum log L_ii
   int* info = nullptr;      // device S
+  double* meta_dev = nullptr;   // device S x 3 : (info, log ml, jitter) per draw, exchanged by the sharded fit
+  bool fac_complete = true;     // fac holds L^-1 of every draw (false after a sharded fit that exchanged the int8 slices only)
   std::vector<char> sliced;   // per draw: facS/sigma hold the slices of the current L^-1
   std::vector<double> jitter;
   std::vector<int> info_host;
@@ -109,6 +117,10 @@ struct b7_blr {
   double* par = nullptr;   // device S x 4: alpha_p, beta, m, 1/beta
   std::vector<double> par_host;
 };
+
+// sharded fit (multi.cu): before / after the exchange of the per-draw state (api.cu)
+int b7_gp_prepare_gather(b7_gp* gp, int s0, int count);
+int b7_gp_finish_gather(b7_gp* gp, bool slices_exchanged);
 
 // stream-ordered pool allocation on the context stream (api.cu)
 int b7_pool_alloc(b7_ctx* ctx, void** p, size_t bytes);

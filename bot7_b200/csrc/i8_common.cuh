@@ -120,20 +120,24 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-// one arrival on the barrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+// one arrival on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics
+// (release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses: `.release.cluster` makes ptxas
+// emit MEMBAR.ALL.GPU + ERRBAR in front of every arrive (measured: 43 % of the relay warp's time, ncu pair_r02).
+// What crosses the pair here is ordered by the barriers themselves: TMA writes complete on the peer's own barrier
+// before the relay arrives, and the tensor core reads them through the async proxy after the leader's wait.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(
                    smem_u32(bar)),
                "r"(cta)
                : "memory");
 }
-// wait with cluster-scope acquire (the arrivals may come from the peer CTA) and a watchdog: a protocol error turns
-// into a trap after ~2 s instead of a hung GPU
+// wait (arrivals may come from the peer CTA) with a watchdog: a protocol error turns into a trap after ~2 s
+// instead of a hung GPU
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
   uint32_t ok = 0;
   unsigned long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
                  : "=r"(ok)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
@@ -143,6 +147,25 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity
     if (t0 == 0) t0 = t;
     else if (t - t0 > 2000000000ULL) __trap();
   }
+}
+
+// tcgen05.ld without the wait: several loads can be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_async(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+}
+// wait for every tcgen05.ld issued so far; the loaded registers are passed through empty asm statements so that the
+// compiler cannot move their first use above the wait
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_pin(uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
 }
 
 // ---- slicing kernels: 512 threads = 128 rows (or columns) x 4 interleaved k quarters --------------------------

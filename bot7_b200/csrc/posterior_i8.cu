@@ -54,6 +54,7 @@ constexpr int B_HALF = NS * TNH * KB;      // 14336 B
 constexpr int P_STAGE = A_STAGE + B_HALF;  // 71680 B
 constexpr int P_NSTAGE = 3;
 constexpr int P_SMEM = P_NSTAGE * P_STAGE + RED_BYTES + 1024;   // 220160 B
+constexpr int P_THREADS = 320;             // warps 0-7 epilogue (lane quadrant w & 3, column half w >> 2), 8 producer, 9 MMA / relay
 static_assert(P_STAGE % 1024 == 0 && P_SMEM <= 227 * 1024, "pair stage geometry");
 
 // ---- slicing -------------------------------------------------------------------------------------------
@@ -247,6 +248,44 @@ __device__ __forceinline__ void epilogue_row_block(uint32_t tmem, int tid, int w
   if (tid < TN && out) out[tid] = ((rr[0 * TN + tid] + rr[1 * TN + tid]) + rr[2 * TN + tid]) + rr[3 * TN + tid];
 }
 
+// The pair kernel's epilogue: 8 warps, warp w drains TMEM lanes 32 (w & 3) .. and the 32 candidate columns of half
+// w >> 2; the 7 class loads go out in batches of 3 + 3 + 1 with one wait per batch (the one-load-one-wait drain of
+// 4 warps kept the accumulators busy for 2.9 us per row block, 6.6 % of the kernel: ncu pair_r02).  Same fma chain
+// per entry and same summation tree as epilogue_row_block: bit-identical results.
+template <typename F>
+__device__ __forceinline__ void epilogue_row_block8(uint32_t tmem, int tid, int warp, int lane, double sc, double* rr, double* out,
+                                                    F arrive_drained) {
+  const int q = warp & 3, hc = warp >> 2;
+  const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hc * 32);
+  double v[32];
+  uint32_t a[3][32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] = 0.0;
+#pragma unroll
+  for (int b0 = 0; b0 < NS; b0 += 3) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (b0 + i < NS) tmem_ld32_async(base + (uint32_t)((b0 + i) * TN), a[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (b0 + i < NS) {
+        tmem_pin(a[i]);
+        const double wt = ldexp(1.0, 4 - 8 * (b0 + i + 2));
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)a[i][c], wt, v[c]);
+      }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) arrive_drained();
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { const double vv = v[c] * sc; v[c] = vv * vv; }
+  rr[q * TN + hc * 32 + lane] = lane_transpose_sum(v, lane);
+  asm volatile("bar.sync 1, 256;\n" ::: "memory");
+  if (tid < TN && out) out[tid] = ((rr[0 * TN + tid] + rr[1 * TN + tid]) + rr[2 * TN + tid]) + rr[3 * TN + tid];
+}
+
 __global__ void __launch_bounds__(I8_THREADS, 1)
 posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, int Np, int NB,
                     const int8_t* __restrict__ ksS, double tau, int chunk, int group, int n_tiles, double* __restrict__ partial) {
@@ -358,7 +397,7 @@ posterior_i8_kernel(const int8_t* __restrict__ facS, const double* __restrict__ 
 // MMA warp waits for both, issues, and commits with a multicast arrive that frees the slot in both CTAs; "accumulators
 // ready" is a multicast commit as well; the 8 epilogue warps of the pair release the accumulators on the leader's
 // acc_empty.  Work items: a tile x pair-chunks (l, P-1-l), P = ceil(NB / 2), 4 (P + 1) stages each.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, int Np, int NB,
                          const int8_t* __restrict__ ksS, double tau, int group, int n_tiles, double* __restrict__ partial, int dbg) {
   // dbg (B7_POST_DBG, measurement only, results are then wrong): 1 = epilogue skips the drain and the fp64 work,
@@ -377,10 +416,10 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
   if (tid == 0) {
     for (int s = 0; s < P_NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(peer_full + s, 1); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);                          // 4 epilogue warps in each CTA of the pair
+    mbar_init(acc_empty, 16);                         // 8 epilogue warps in each CTA of the pair
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
   }
@@ -390,7 +429,7 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---- producer (both CTAs): own row block + own half of the candidate tile ----
     int slot = 0;
     unsigned phase = 1;
@@ -419,7 +458,7 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
           }
         }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     int slot = 0, done = 0;
     unsigned phase = 0;
     if (rank == 0) {
@@ -475,7 +514,7 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
             }
     }
   } else {
-    // ---- epilogue warps 0-3 of both CTAs: CTA `rank` holds row block 2j + rank in its TMEM ----
+    // ---- epilogue warps 0-7 of both CTAs: CTA `rank` holds row block 2j + rank in its TMEM ----
     int done = 0;
     for (int item = pair_id; item < wk.n_items(); item += n_pairs) {
       const int tile = wk.tile(item);
@@ -490,8 +529,8 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
             if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
             continue;
           }
-          const double sc = rb < NB ? sigma[rb * TM + tid] * tau : 0.0;
-          epilogue_row_block(tmem, tid, warp, lane, sc, red + (done & 1) * (4 * TN),
+          const double sc = rb < NB ? sigma[rb * TM + (tid & 127)] * tau : 0.0;
+          epilogue_row_block8(tmem, tid, warp, lane, sc, red + (done & 1) * (4 * TN),
                              rb < NB ? partial + ((long long)tile * NB + rb) * TN : nullptr, [&] { mbar_arrive_cluster(acc_empty, 0); });
         }
     }
@@ -499,7 +538,7 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                 // nobody leaves while the peer may still read its shared memory
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
 }
 
 // var = sf2 - sum_rb sum v^2 (row blocks added in ascending order), mean = m + tau 2^-54 sum_kb meanP (column blocks
@@ -603,7 +642,7 @@ int b7_launch_posterior_i8(b7_ctx* ctx, const int8_t* facS, const double* sigma,
   if (ctx->post_pair) {
     const int P = (NB + 1) / 2, n_items = n_tiles * ((P + 1) / 2), n_pairs = ctx->sm_count / 2;
     static const int dbg_env = getenv("B7_POST_DBG") ? atoi(getenv("B7_POST_DBG")) : 0;
-    posterior_i8_pair_kernel<<<2 * (n_items < n_pairs ? n_items : n_pairs), I8_THREADS, P_SMEM, ctx->stream>>>(facS, sigma, Np, NB, ksS, tau, group,
+    posterior_i8_pair_kernel<<<2 * (n_items < n_pairs ? n_items : n_pairs), P_THREADS, P_SMEM, ctx->stream>>>(facS, sigma, Np, NB, ksS, tau, group,
                                                                                                               n_tiles, partial, dbg_env);
   } else {
     static const int chunk_env = getenv("B7_POST_CHUNK") ? atoi(getenv("B7_POST_CHUNK")) : 0;

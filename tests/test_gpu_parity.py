@@ -724,6 +724,81 @@ def test_sharded_acquisition_equals_single(ctx, oracle):
     f.free()
 
 
+def _two_gpus():
+    return L.lib().b7_device_count() >= 2
+
+
+@pytest.mark.parametrize("S,path", [(8, L.PATH_INT8_OZAKI), (5, L.PATH_INT8_OZAKI), (4, L.PATH_FP64_DMMA)])
+def test_multi_gpu_c_abi_equals_single_gpu(ctx, oracle, S, path):
+    """(e) on real GPUs, through the C ABI only: b7_comm_init_all over every device of the box, Sobol shards generated
+    per device, draw-sharded fit + NCCL exchange inside the library (all-gather when S divides, broadcasts otherwise),
+    shard scoring and the (best, index, nan) combine -- must reproduce the one-GPU result bit for bit: log marginal
+    likelihoods, every score, the selected candidate and the grid row it removes (bots/bayesopt.lua:56-99, bots/abstract.lua:118)."""
+    if not _two_gpus():
+        pytest.skip("needs at least 2 GPUs")
+    G = min(L.lib().b7_device_count(), 8)
+    N, d, M = 700, 6, 30011
+    pts = oracle.sobol_points(d, N + M)
+    Xo = pts[:N]
+    y = oracle.hartmann6(Xo)
+    y = (y - y.mean()) / y.std()
+    r = np.random.default_rng(S)
+    hyp = np.zeros((S, d + 3))
+    hyp[:, :d] = np.log(0.15) + r.random((S, d)) * np.log(8)
+    hyp[:, d + 1] = 0.5 * np.log(1e-2)
+    fmin = float(y.min())
+    keep = ctx.posterior_path()
+    comm = parallel.Comm.all(G)
+    try:
+        ctx.set_posterior_path(path)
+        for c in comm.ctxs:
+            c.set_posterior_path(path)
+        f = models.GPFactors(Xo, y, hyp)
+        g1 = grids.sobol({"size": N + M, "dims": d}).generate_device(first=N, count=M)
+        one = np.empty(M)
+        am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+        L.check(L.lib().b7_acq_score(f.handle, g1.handle, L.SCORE_EI, 0.0, 0, -1.0, fmin, L.dptr(one), C.byref(am), C.byref(amo),
+                                     C.byref(best), C.byref(nn)))
+        gs = comm.sobol_grid(d, 1 + N, M)
+        assert sum(g.rows() for g in gs) == M
+        gps, info, logml, jit, gather_ms = comm.fit(Xo, y, hyp)
+        assert (info == 0).all() and np.array_equal(logml, f.logml)
+        b, a, ao, n_, sc = comm.acq_score(gps, gs, L.SCORE_EI, 0.0, 0, -1.0, fmin, want_scores=True)
+        assert np.array_equal(sc, one)                                   # every score, bit for bit
+        assert (b, a, ao, n_) == (best.value, am.value, amo.value, nn.value)
+        # steal the nominated row on both, score again: compacted numbering stays global
+        row_m = comm.grid_remove(gs, a)
+        row_1 = g1.remove(am.value)
+        assert np.array_equal(row_m, row_1.reshape(-1))
+        L.check(L.lib().b7_acq_score(f.handle, g1.handle, L.SCORE_EI, 0.0, 0, -1.0, fmin, None, C.byref(am), C.byref(amo), C.byref(best),
+                                     C.byref(nn)))
+        b, a, ao, n_, _ = comm.acq_score(gps, gs, L.SCORE_EI, 0.0, 0, -1.0, fmin)
+        assert (b, a, ao, n_) == (best.value, am.value, amo.value, nn.value)
+        comm.free_fit(gps)
+        for g in gs:
+            g.free()
+        g1.free()
+        f.free()
+    finally:
+        ctx.set_posterior_path(keep)
+        comm.close()
+
+
+def test_multi_gpu_one_process_per_gpu(ctx):
+    """The same exchange with one process per GPU (torchrun): b7_comm_unique_id / b7_comm_init_rank, the unique id
+    carried by torch.distributed (gloo); rank 0 compares against its own one-GPU result (tools/multi_check.py)."""
+    if not _two_gpus():
+        pytest.skip("needs at least 2 GPUs")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    G = min(L.lib().b7_device_count(), 8)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={G}", "--master-addr", "127.0.0.1",
+                          "--master-port", "29517", os.path.join(root, "tools", "multi_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "multi_check ok" in out.stdout
+
+
 # ---------------------------------------------------------------------------------- grid bookkeeping
 
 def test_grid_compaction_semantics(ctx):
