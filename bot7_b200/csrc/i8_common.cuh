@@ -149,6 +149,25 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity
   }
 }
 
+// L2 eviction-priority hints for the bulk copies: the slices of L^-1 are re-read by every CTA pair for the whole
+// launch (evict_last), a candidate tile's K* slices are streamed (evict_first / normal)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // tcgen05.ld without the wait: several loads can be in flight before one tmem_ld_wait()
 __device__ __forceinline__ void tmem_ld32_async(uint32_t addr, uint32_t (&v)[32]) {
   asm volatile(

@@ -401,7 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restrict__ sigma, int Np, int NB,
                          const int8_t* __restrict__ ksS, double tau, int group, int n_tiles, double* __restrict__ partial, int dbg) {
   // dbg (B7_POST_DBG, measurement only, results are then wrong): 1 = epilogue skips the drain and the fp64 work,
-  // 2 = producers always fetch the first stage of the first tile (every copy hits the same hot L2 lines)
+  // 2 = producers always fetch the first stage of the first tile (every copy hits the same hot L2 lines),
+  // 4 = producers fetch 2 KB per stage (no operand traffic to speak of)
   extern __shared__ __align__(1024) uint8_t smem[];
   double* red = reinterpret_cast<double*>(smem + P_NSTAGE * P_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_NSTAGE * P_STAGE + RED_BYTES);
@@ -431,6 +432,7 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
 
   if (warp == 8) {
     // ---- producer (both CTAs): own row block + own half of the candidate tile ----
+    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
     int slot = 0;
     unsigned phase = 1;
     bool wrapped = false;
@@ -444,13 +446,24 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
             if (wrapped) mbar_wait_cluster(empty + slot, phase);
             if (elect_one()) {
               uint8_t* st = smem + slot * P_STAGE;
+              if (dbg & 4) {                         // 2 KB instead of 71.7 KB per stage: the MMAs run on stale operands
+                mbar_arrive_expect_tx(full + slot, 2048);
+                bulk_g2s(st, facS, 1024, full + slot);
+                bulk_g2s(st + A_STAGE, ksS, 1024, full + slot);
+                __syncwarp();
+                if (++slot == P_NSTAGE) { slot = 0; phase ^= 1u; wrapped = true; }
+                continue;
+              }
               mbar_arrive_expect_tx(full + slot, P_STAGE);
               if (dbg & 2) {
                 bulk_g2s(st, facS, A_STAGE, full + slot);
                 bulk_g2s(st + A_STAGE, ksS, B_HALF, full + slot);
               } else {
-                bulk_g2s(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot);
-                bulk_g2s(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot);
+                const int hint = dbg >> 4;      // measurement knob: 1 = L^-1 evict_last, 2 = + K* evict_first, 3 = K* evict_first only
+                if (hint == 1 || hint == 2) bulk_g2s_hint(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot, pol_last);
+                else bulk_g2s(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot);
+                if (hint == 2 || hint == 3) bulk_g2s_hint(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot, pol_first);
+                else bulk_g2s(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot);
               }
             }
             __syncwarp();
