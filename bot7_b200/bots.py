@@ -34,8 +34,11 @@ class abstract:
             if cache.get("candidates") is not None:
                 self.grid = Grids.DeviceGrid.from_host(cache["candidates"], ctx)
             else:
-                g = getattr(Grids, config["grid"]["type"])(config["grid"])
-                self.grid = g.generate_device()
+                gtype = config["grid"]["type"]
+                if gtype == "random":
+                    self.grid = Grids.random(config["grid"], self.rng).generate_device(ctx=ctx)
+                else:
+                    self.grid = getattr(Grids, gtype)(config["grid"], ctx).generate_device()
         self.responses = cache.get("responses")
         self.observed = cache.get("observed")
         self.pending = None
@@ -194,10 +197,12 @@ class bayesopt(abstract):
         M = self.grid.rows()
         score = np.empty(M) if want_score else None
         am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
-        L.check(L.lib().b7_acq_score(f.handle, self.grid.handle, kind, tradeoff, bound, sign, fmin,
-                                     L.dptr(score) if want_score else None, C.byref(am), C.byref(amo), C.byref(best),
-                                     C.byref(nn)), "b7_acq_score")
-        f.free()
+        try:
+            L.check(L.lib().b7_acq_score(f.handle, self.grid.handle, kind, tradeoff, bound, sign, fmin,
+                                         L.dptr(score) if want_score else None, C.byref(am), C.byref(amo), C.byref(best),
+                                         C.byref(nn)), "b7_acq_score")
+        finally:
+            f.free()                                                 # multi-GB of factors: not left to the GC on an error
         self.last = {"argmax": am.value, "argmax_original": amo.value, "best": best.value, "nan_count": nn.value}
         if want_score:
             score = score[self._live_mask(M)]                        # compacted numbering, like the reference

@@ -16,6 +16,7 @@
 //        global reads are coalesced) and does D^2/2 FMAs: on B200 (5.8 flop per HBM byte) that is
 //        balanced between the FP64 pipe and HBM for D = 50.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -23,6 +24,10 @@
 #include "b7_internal.h"
 
 int b7_score_grid_size(b7_ctx* ctx, int64_t M);
+// blr_dmma.cu: MLP basis + BLR head on DMMA tiles; returns 1 when the shapes do not fit (use the kernels below)
+int b7_launch_dngo_tiles(b7_ctx* ctx, const double* in, int64_t M, int n_layers, const int* dims, const double* const* W_dev,
+                         const double* const* b_dev, int relu_last, const double* Linv, const double* w, const double* par, int D, int S,
+                         int64_t ld_out, double* mean, double* var, double* feat_out);
 
 namespace {
 
@@ -214,6 +219,19 @@ int launch_moments(b7_ctx* ctx, const double* Z, int64_t M, const b7_blr* blr, i
                    double* var) {
   if (M <= 0) return 0;
   const int D = blr->D, dp = (D + 7) / 8 * 8;
+  static const bool tiles = !(getenv("B7_BLR_DMMA") && getenv("B7_BLR_DMMA")[0] == '0');
+  if (tiles) {
+    // DMMA tiles (blr_dmma.cu); the draws are staged in shared memory in chunks (4, 2 or 1 draws, whatever fits)
+    int rc = 0, chunk = 4;
+    for (int c0 = 0; c0 < S && rc == 0;) {
+      const int sc = std::min(chunk, S - c0);
+      rc = b7_launch_dngo_tiles(ctx, Z, M, 0, &D, nullptr, nullptr, 0, blr->Linv + (size_t)(s0 + c0) * D * D, blr->w + (size_t)(s0 + c0) * D,
+                                blr->par + (size_t)(s0 + c0) * 4, D, sc, ld_out, mean + (size_t)c0 * ld_out, var + (size_t)c0 * ld_out, nullptr);
+      if (rc == 1 && chunk > 1 && c0 == 0) { chunk /= 2; rc = 0; continue; }
+      c0 += sc;
+    }
+    if (rc <= 0) return rc;
+  }
   switch (dp) {
     case 8: return launch_moments_dp<8>(ctx, Z, M, D, blr, s0, S, ld_out, mean, var);
     case 16: return launch_moments_dp<16>(ctx, Z, M, D, blr, s0, S, ld_out, mean, var);
@@ -306,6 +324,35 @@ struct Part {
   ~Part() { b7_pool_free(ctx, best); b7_pool_free(ctx, idx); b7_pool_free(ctx, nan); }
 };
 
+// device copies of the layer weights for one call (freed when the call returns)
+struct DevWeights {
+  b7_ctx* ctx;
+  std::vector<const double*> W, b;
+  std::vector<double*> owned;
+  explicit DevWeights(b7_ctx* c) : ctx(c) {}
+  ~DevWeights() { for (double* p : owned) b7_pool_free(ctx, p); }
+  int upload(int n_layers, const int* dims, const double* const* Wh, const double* const* bh) {
+    for (int l = 0; l < n_layers; ++l) {
+      double *dW = nullptr, *db = nullptr;
+      B7_CHECK(dalloc(ctx, &dW, (size_t)dims[l] * dims[l + 1]));
+      owned.push_back(dW);
+      B7_CHECK(dalloc(ctx, &db, (size_t)dims[l + 1]));
+      owned.push_back(db);
+      B7_CUDA(cudaMemcpyAsync(dW, Wh[l], (size_t)dims[l] * dims[l + 1] * 8, cudaMemcpyHostToDevice, ctx->stream));
+      B7_CUDA(cudaMemcpyAsync(db, bh[l], (size_t)dims[l + 1] * 8, cudaMemcpyHostToDevice, ctx->stream));
+      W.push_back(dW);
+      b.push_back(db);
+    }
+    B7_CUDA(cudaStreamSynchronize(ctx->stream));     // the host arrays are borrowed for the duration of the call only
+    return 0;
+  }
+};
+
+bool mlp_tiles_enabled() {
+  static const bool on = !(getenv("B7_BLR_DMMA") && getenv("B7_BLR_DMMA")[0] == '0');
+  return on;
+}
+
 }  // namespace
 
 extern "C" {
@@ -317,10 +364,35 @@ int b7_mlp_features(b7_ctx* ctx, b7_grid* in, int n_layers, const int* dims, con
     return B7_ERR_ARG;
   }
   *out = nullptr;
+  if (in->ctx != ctx) { b7_set_error("mlp_features: the grid lives on another context / device"); return B7_ERR_ARG; }
   for (int l = 0; l <= n_layers; ++l)
     if (dims[l] < 1 || dims[l] > 64) { b7_set_error("mlp_features: layer widths must be in [1, 64] (got %d)", dims[l]); return B7_ERR_ARG; }
   B7_CUDA(cudaSetDevice(ctx->device));
   const int64_t M = in->rows;
+  double* feat = nullptr;
+  {
+    // all layers in one pass over the grid on DMMA tiles (blr_dmma.cu): the intermediate activations stay in shared memory
+    DevWeights dw(ctx);
+    B7_CHECK(dw.upload(n_layers, dims, W, b));
+    B7_CHECK(dalloc(ctx, &feat, (size_t)std::max<int64_t>(M, 1) * dims[n_layers]));
+    StageTimer t(ctx, ST_BLR);
+    int rc_t = mlp_tiles_enabled() ? b7_launch_dngo_tiles(ctx, in->X, M, n_layers, dims, dw.W.data(), dw.b.data(), relu_last, nullptr, nullptr, nullptr,
+                                                          0, 0, 0, nullptr, nullptr, feat)
+                                   : 1;
+    t.stop(1);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc_t == 0 && e != cudaSuccess) { b7_set_error("mlp_features: %s", cudaGetErrorString(e)); rc_t = B7_ERR_CUDA; }
+    if (rc_t < 0) { b7_pool_free(ctx, feat); return rc_t; }
+    if (rc_t == 0) {
+      b7_grid* g = new b7_grid();
+      g->ctx = ctx; g->rows = M; g->d = dims[n_layers]; g->X = feat;
+      g->removed = in->removed;            // the feature grid inherits the candidate bookkeeping
+      g->removed_dirty = !g->removed.empty();
+      *out = g;
+      return 0;
+    }
+    b7_pool_free(ctx, feat);
+  }
   const double* cur = in->X;
   double* bufs[2] = {nullptr, nullptr};
   int rc = 0;
@@ -450,12 +522,16 @@ int b7_blr_predict(b7_blr* blr, int s, const double* Z1, int64_t M, double* mean
   return rc;
 }
 
-int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int bound, double sign, double fmin,
-                 double* score_host, int64_t* argmax, int64_t* argmax_original, double* best, int64_t* nan_count) {
-  if (!blr || !features || features->d != blr->D || (kind != B7_SCORE_EI && kind != B7_SCORE_CB)) {
+// shared body of b7_blr_score (n_layers = 0: `features` already holds the basis) and b7_dngo_score (the basis is
+// evaluated tile by tile in front of the head and never stored)
+static int blr_score_impl(b7_blr* blr, b7_grid* features, int n_layers, const int* dims, const double* const* W, const double* const* b,
+                          int relu_last, int kind, double tradeoff, int bound, double sign, double fmin, double* score_host, int64_t* argmax,
+                          int64_t* argmax_original, double* best, int64_t* nan_count) {
+  if (!blr || !features || (kind != B7_SCORE_EI && kind != B7_SCORE_CB) || (n_layers == 0 && features->d != blr->D)) {
     b7_set_error("blr_score: bad arguments (feature dims %d vs D %d)", features ? features->d : -1, blr ? blr->D : -1);
     return B7_ERR_ARG;
   }
+  if (features->ctx != blr->ctx) { b7_set_error("blr_score: the feature grid and the model live on different contexts / devices"); return B7_ERR_ARG; }
   b7_ctx* ctx = blr->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
   const int64_t M = features->rows;
@@ -477,10 +553,28 @@ int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int 
     features->removed_dirty = false;
   }
   int rc = 0, parts = 0;
-  {
+  if (n_layers == 0) {
     StageTimer t(ctx, ST_BLR);
     rc = launch_moments(ctx, features->X, M, blr, 0, S, M, mom, mom + (size_t)S * M);
     t.stop(1);
+  } else {
+    DevWeights dw(ctx);
+    if ((rc = dw.upload(n_layers, dims, W, b)) == 0) {
+      StageTimer t(ctx, ST_BLR);
+      const int D = blr->D;
+      int chunk = 4;
+      for (int c0 = 0; c0 < S && rc == 0;) {
+        const int sc_ = std::min(chunk, S - c0);
+        rc = b7_launch_dngo_tiles(ctx, features->X, M, n_layers, dims, dw.W.data(), dw.b.data(), relu_last, blr->Linv + (size_t)c0 * D * D,
+                                  blr->w + (size_t)c0 * D, blr->par + (size_t)c0 * 4, D, sc_, M, mom + (size_t)c0 * M,
+                                  mom + (size_t)(S + c0) * M, nullptr);
+        if (rc == 1 && chunk > 1 && c0 == 0) { chunk /= 2; rc = 0; continue; }
+        c0 += sc_;
+      }
+      t.stop(1);
+      cudaStreamSynchronize(ctx->stream);              // dw's buffers are released when this scope ends
+      if (rc == 1) { b7_set_error("dngo_score: layer shapes do not fit the tile kernel (widths <= 63, at most 4 layers)"); rc = B7_ERR_ARG; }
+    }
   }
   if (rc == 0 && M > 0) {
     StageTimer t(ctx, ST_SCORE);
@@ -514,6 +608,23 @@ int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int 
   if (best) *best = orig ? bv : NAN;
   if (nan_count) *nan_count = nn;
   return 0;
+}
+
+int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int bound, double sign, double fmin,
+                 double* score_host, int64_t* argmax, int64_t* argmax_original, double* best, int64_t* nan_count) {
+  return blr_score_impl(blr, features, 0, nullptr, nullptr, nullptr, 0, kind, tradeoff, bound, sign, fmin, score_host, argmax, argmax_original,
+                        best, nan_count);
+}
+
+int b7_dngo_score(b7_blr* blr, b7_grid* grid, int n_layers, const int* dims, const double* const* W, const double* const* b, int relu_last,
+                  int kind, double tradeoff, int bound, double sign, double fmin, double* score_host, int64_t* argmax,
+                  int64_t* argmax_original, double* best, int64_t* nan_count) {
+  if (!grid || n_layers < 1 || !dims || !W || !b || dims[0] != grid->d || !blr || dims[n_layers] != blr->D) {
+    b7_set_error("dngo_score: bad arguments (dims[0] must equal the grid's dims, dims[n_layers] the head's D)");
+    return B7_ERR_ARG;
+  }
+  return blr_score_impl(blr, grid, n_layers, dims, W, b, relu_last, kind, tradeoff, bound, sign, fmin, score_host, argmax, argmax_original, best,
+                        nan_count);
 }
 
 }  // extern "C"

@@ -305,6 +305,24 @@ def mlp_features(grid, weights, biases, relu_last=True, ctx=None):
     return DeviceGrid(out, ctx)
 
 
+def dngo_score(blr, grid, weights, biases, relu_last=True, kind=L.SCORE_EI, tradeoff=0.0, bound=0, sign=-1.0, fmin=0.0,
+               want_scores=False):
+    """dngo:predict + score + argmax over a device grid in one pass (b7_dngo_score; models/dngo.lua:155-174): the basis is
+    evaluated in front of the BLR head tile by tile, the feature matrix Z1 is never stored.
+    Returns (scores or None, argmax (compacted), argmax_original, best, nan_count)."""
+    Ws = [L.as_f64(w) for w in weights]
+    bs = [L.as_f64(b).reshape(-1) for b in biases]
+    n = len(Ws)
+    dims = (C.c_int * (n + 1))(*([Ws[0].shape[1]] + [w.shape[0] for w in Ws]))
+    Wp = (C.POINTER(C.c_double) * n)(*[L.dptr(w) for w in Ws])
+    bp = (C.POINTER(C.c_double) * n)(*[L.dptr(b) for b in bs])
+    sc = np.empty(grid.rows()) if want_scores else None
+    am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+    L.check(L.lib().b7_dngo_score(blr.handle, grid.handle, n, dims, Wp, bp, int(bool(relu_last)), kind, tradeoff, bound, sign, fmin,
+                                  L.dptr(sc), C.byref(am), C.byref(amo), C.byref(best), C.byref(nn)), "b7_dngo_score")
+    return sc, am.value, amo.value, best.value, nn.value
+
+
 class bayes_linear:
     """gp.models.bayes_linear as used by models/dngo.lua:77-79,174:
     predict(Z0, Y0, Z1, nil, hyp, req) with hyp == 'marginalize' or a S x 3 array."""

@@ -158,6 +158,12 @@ int b7_blr_predict(b7_blr* blr, int s, const double* Z1, int64_t M, double* mean
 int b7_blr_score(b7_blr* blr, b7_grid* features, int kind, double tradeoff, int bound, double sign,
                  double fmin, double* score_host, int64_t* argmax, int64_t* argmax_original,
                  double* best, int64_t* nan_count);
+/* dngo:predict on the candidate grid in one pass (models/dngo.lua:155-174): the basis (same arguments as
+ * b7_mlp_features, widths <= 63) is evaluated tile by tile in shared memory in front of the BLR head, so the M x D
+ * feature matrix Z1 is never stored; then the same scoring / average / argmax as b7_blr_score. */
+int b7_dngo_score(b7_blr* blr, b7_grid* grid, int n_layers, const int* dims, const double* const* W,
+                  const double* const* b, int relu_last, int kind, double tradeoff, int bound, double sign, double fmin,
+                  double* score_host, int64_t* argmax, int64_t* argmax_original, double* best, int64_t* nan_count);
 void b7_blr_free(b7_blr* blr);
 
 /* ---- multi-GPU: candidate shards + draw-sharded fit (bots/bayesopt.lua:56-99 over config.bot.nGPU devices) ----

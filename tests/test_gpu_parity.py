@@ -893,8 +893,48 @@ def test_dngo_device_pipeline(ctx, oracle):
     assert rel(sc[live], ref[live], 1e-6 * ref[live].max()) <= 1e-7
     b, i, n = oracle.argmax_first(np.where(live, ref, np.nan))
     assert amo.value == i and am.value == i - (1 if i > 123 else 0)
+    # dngo:predict in one pass (b7_dngo_score): the basis is evaluated tile by tile in front of the head and Z1 is never
+    # stored; same scores as the two-step path to rounding, same selected candidate
+    sc2, am2, amo2, best2, nn2 = models.dngo_score(f, grid, Ws, bs, True, L.SCORE_EI, 0.0, 0, -1.0, fmin, want_scores=True)
+    assert np.isnan(sc2[122]) and rel(sc2[live], ref[live], 1e-6 * ref[live].max()) <= 1e-7
+    assert rel(sc2[live], sc[live], 1e-6 * ref[live].max()) <= 1e-12
+    assert (am2, amo2) == (am.value, amo.value) and abs(best2 - best.value) <= 1e-12 * abs(best.value)
     with pytest.raises(L.B7Error, match="widths"):
         models.mlp_features(grid, [r.normal(size=(65, d))], [np.zeros(65)])
+    f.free()
+
+
+@pytest.mark.parametrize("D,S,layers", [(1, 1, (3,)), (7, 3, (4, 9)), (50, 5, (6,)), (63, 3, (20, 33, 40)), (64, 1, (6,))])
+def test_dngo_tile_kernel_shapes_vs_oracle(ctx, oracle, D, S, layers):
+    # DMMA tile kernels (blr_dmma.cu) at ragged widths: 1, below / above a fragment, the 63-wide limit of the head, more than
+    # 4 draws (chunked), and D = 64 (falls back to the per-candidate kernels); ragged candidate counts (last tile partial)
+    r = np.random.default_rng(D * 7 + S)
+    dims = list(layers) + [D]
+    Ws = [r.normal(size=(dims[i + 1], dims[i])) / np.sqrt(dims[i]) for i in range(len(dims) - 1)]
+    bs = [0.1 * r.normal(size=dims[i + 1]) for i in range(len(dims) - 1)]
+    N, M = 300, 128 * 37 + 5
+    Xo, Xc = r.random((N, dims[0])), r.random((M, dims[0]))
+    y = r.normal(size=N)
+    Z0, Zref = oracle.mlp_features(Xo, Ws, bs), oracle.mlp_features(Xc, Ws, bs)
+    hyp = np.stack([np.array([np.log(0.5 + s), np.log(20.0 + 10 * s), 0.05 * s]) for s in range(S)])
+    f = models.BLRFactors(Z0, y, hyp)
+    grid = grids.DeviceGrid.from_host(Xc)
+    feats = models.mlp_features(grid, Ws, bs)
+    assert np.max(np.abs(feats.read() - Zref)) <= 1e-12 * max(1.0, np.max(np.abs(Zref)))
+    for s in range(S):
+        mu, var = f.predict(s, Zref)
+        mr, vr = oracle.blr_predict(oracle.blr_fit(Z0, y, hyp[s]), Zref)
+        assert rel(mu, mr, 1.0) <= 1e-10 and rel(var, vr, 1e-300) <= 1e-9
+    fmin = float(y.min())
+    per = [oracle.ei_compute(*oracle.blr_predict(oracle.blr_fit(Z0, y, hyp[s]), Zref), fmin, 0.0) for s in range(S)]
+    ref = oracle.mc_average(per)
+    b, i, n = oracle.argmax_first(ref)
+    if D <= 63:
+        sc, am, amo, best, nn = models.dngo_score(f, grid, Ws, bs, True, L.SCORE_EI, 0.0, 0, -1.0, fmin, want_scores=True)
+        assert rel(sc, ref, 1e-6 * max(ref.max(), 1e-300)) <= 1e-7 and am == i
+    else:
+        with pytest.raises(L.B7Error, match="tile kernel"):
+            models.dngo_score(f, grid, Ws, bs, True, L.SCORE_EI, 0.0, 0, -1.0, fmin)
     f.free()
 
 
