@@ -52,12 +52,13 @@ int dev_alloc_bytes(b7_ctx* ctx, void** p, size_t bytes) {
         ctx->live[*p] = bytes;
         return 0;
       }
-  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  cudaError_t e = cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
   if (e != cudaSuccess && !ctx->cache.empty()) {          // give the cached blocks back and try again
     cudaGetLastError();
     cache_flush(ctx);
     cudaStreamSynchronize(ctx->stream);
-    e = cudaMallocAsync(p, bytes, ctx->stream);
+    cudaMemPoolTrimTo(ctx->pool, 0);
+    e = cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -224,11 +225,24 @@ int b7_init(int device, b7_ctx** out) {
     B7_CUDA(cudaEventCreateWithFlags(&ctx->evP[i], cudaEventDisableTiming));
   }
   { const char* e = getenv("B7_KSTAR_OVERLAP"); ctx->kstar_overlap = !(e && e[0] == '0'); }
-  cudaMemPool_t pool;
-  B7_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  unsigned long long keep = ~0ULL;   // never trim: freed buffers stay in the pool for the next fit
-  B7_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  { size_t free_b = 0, total_b = 0; B7_CUDA(cudaMemGetInfo(&free_b, &total_b)); ctx->cache_cap = total_b / 3; }
+  // a pool of this context's own (the device's default pool, which torch or NCCL in the same process may use, keeps its
+  // settings); never trimmed while the context lives: freed buffers stay in the pool for the next fit
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  B7_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+  unsigned long long keep = ~0ULL;
+  B7_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  // exact-size block cache in front of the pool: at most B7_CACHE_FRACTION (default 1/3) of the device memory
+  {
+    size_t free_b = 0, total_b = 0;
+    B7_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const char* e = getenv("B7_CACHE_FRACTION");
+    const double frac = e ? atof(e) : 1.0 / 3.0;
+    ctx->cache_cap = (size_t)((frac < 0.0 ? 0.0 : (frac > 0.9 ? 0.9 : frac)) * (double)total_b);
+  }
   { const char* e = getenv("B7_POSTERIOR_I8"); ctx->use_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_POTRF_I8"); ctx->potrf_i8 = !(e && e[0] == '0'); }
   { const char* e = getenv("B7_TRTRI_I8"); ctx->trtri_i8 = !(e && e[0] == '0'); }
@@ -252,7 +266,6 @@ void b7_shutdown(b7_ctx* ctx) {
   cache_flush(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->stream2);
-  { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->evK[i]); cudaEventDestroy(ctx->evP[i]); }
@@ -262,6 +275,7 @@ void b7_shutdown(b7_ctx* ctx) {
   cudaEventDestroy(ctx->tm0);
   cudaEventDestroy(ctx->tm1);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
 }
 

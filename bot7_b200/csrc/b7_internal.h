@@ -35,6 +35,7 @@ struct b7_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;                   // private stream-ordered pool: the device's default pool is left alone
   cudaStream_t stream2 = nullptr;                 // far trailing updates of the Cholesky (overlaps the next panel)
   cudaEvent_t evA = nullptr, evB = nullptr;
   cudaEvent_t evK[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};   // K* pass of draw s + 1 under the posterior pass of draw s

@@ -54,14 +54,24 @@ __device__ __forceinline__ void frag_mac(double& c0, double& c1, const double* _
 }
 
 // 1/sqrt(x) without the library's out-of-line slow path (its CALL forces the 16 row registers of the
-// factorisation below through local memory): float seed + three Newton steps, <= 2 ulp for normal x;
-// x <= 0 or NaN gives inf / NaN, which is what the info logic wants to see propagate.
+// factorisation below through local memory): float seed + three Newton steps, <= 2 ulp for normal x.
+// A normal positive x is first scaled by an even power of two into [1, 4) (exact, on the exponent bits), so that a
+// pivot above FLT_MAX or below FLT_MIN no longer loses the float seed (inf -> seed 0 -> result 0; denormal -> NaN);
+// x <= 0, NaN, inf or denormal keeps the plain path and gives inf / NaN / 0, which the info logic flags.
 __device__ __forceinline__ double rsqrt_nr(double x) {
-  double y = (double)rsqrtf((float)x);
-  const double hx = 0.5 * x;
+  const long long bits = __double_as_longlong(x);
+  const int ef = (int)((bits >> 52) & 0x7ff);
+  double m = x, scale = 1.0;
+  if (bits > 0 && ef >= 1 && ef <= 2046) {
+    const int e2 = (ef - 1023) & ~1;                                        // even, rounds towards -inf
+    m = __longlong_as_double(bits - ((long long)e2 << 52));                 // x 2^-e2 in [1, 4)
+    scale = __longlong_as_double((long long)(1023 - e2 / 2) << 52);         // 2^(-e2 / 2)
+  }
+  double y = (double)rsqrtf((float)m);
+  const double hx = 0.5 * m;
 #pragma unroll
   for (int it = 0; it < 3; ++it) y = y * fma(-hx * y, y, 1.5);
-  return y;
+  return y * scale;
 }
 
 // ---- diagonal block: potf2 + inverse + x_j + logdet + info -------------------------------------
@@ -110,7 +120,8 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
         if (lane == 0) {
           pivs[j0 + q] = piv;
           invs[j0 + q] = inv;
-          if (!(piv > 0.0) && my_info == 0) my_info = j * NBK + j0 + q + 1;
+          // LAPACK info: first pivot that is not positive -- or whose reciprocal root is not a finite positive number
+          if ((!(piv > 0.0) || !(inv > 0.0) || inv > 1.79e308) && my_info == 0) my_info = j * NBK + j0 + q + 1;
         }
         const double my = a[q] * inv;   // L[lane][q] for lane > q
 #pragma unroll
