@@ -574,6 +574,7 @@ static int gp_slice(b7_gp* gp, int s0, int count) {
 
 static int gp_invert(b7_gp* gp, int s0, int count) {
   b7_ctx* ctx = gp->ctx;
+  if (count <= 0) return 0;            // a rank of a sharded fit that owns no draw (S < number of GPUs)
   StageTimer t(ctx, ST_TRTRI);
   int64_t before = ctx->launches;
   // alpha = L^-T beta while L is still there (the INT8 path's mean is the fp64 dot product k*^T alpha)

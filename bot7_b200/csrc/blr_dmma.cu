@@ -51,20 +51,56 @@ struct Ptrs {
   const double* b[MAXL];
 };
 
-// acc[i][j] (+)= A[8i.., k] * B[cand.., k]^T over k < K4; A: rows x lda, Bt: [cand][ldb]
-__device__ __forceinline__ void tile_mma(const double* __restrict__ A, int lda, int mf, int K4, const double* __restrict__ Bt, int ldb,
-                                         int lane, double (&acc)[MAXF][2][2], bool tri, int dense_frag) {
+// acc[i][j] (+)= A[8i.., k] * B[cand.., k]^T over k < K4; A: rows x lda, Bt: [cand][ldb].
+// MF (output fragments) is a compile-time constant so that the fragment loop carries no branches: the loads of a pair of
+// k-steps (up to 2 x 7 A fragments + 4 B fragments) are issued together in front of their up to 28 DMMAs (with a runtime
+// bound and `break` in the loop every fragment load sat in front of its own two DMMAs: 28 % of the DMMA issue rate).
+// tri: A is [L^-1 ; w^T] -- fragment i is zero for k > 8 i + 7, except the last one (it holds the dense row w^T), so the
+// fragments active at k0 are the suffix i >= k0 / 8.
+template <int MF>
+__device__ __forceinline__ void tile_mma_t(const double* __restrict__ A, int lda, int K4, const double* __restrict__ Bt, int ldb, int lane,
+                                           double (&acc)[MAXF][2][2], bool tri) {
   const int r = lane >> 2, c = lane & 3;
+  const double* Ar = A + r * lda + c;
+  const double* B0 = Bt + r * ldb + c;
+  const double* B1 = Bt + (8 + r) * ldb + c;
+  // Fragments i >= first are active at this pair of k-steps.  The skip is a real (warp-uniform) jump into a fall-through
+  // switch: a predicated-off DMMA still holds the FP64 tensor pipe for its 16 cycles (ncu dngo_r02: 47.7 M DMMAs issued,
+  // 28.8 M predicated on, pipe busy for all of them).
+#define B7_FRAG_LOAD(I, KK)                                                  \
+  if (MF > I) { av[I] = Ar[8 * I * lda + KK]; }
+#define B7_FRAG_MMA(I, BA, BB)                                               \
+  if (MF > I) { dmma884(acc[I][0][0], acc[I][0][1], av[I], BA); dmma884(acc[I][1][0], acc[I][1][1], av[I], BB); }
+#define B7_FRAG_SWITCH(OP, ...)                                              \
+  switch (first) {                                                           \
+    case 0: OP(0, ##__VA_ARGS__) case 1: OP(1, ##__VA_ARGS__) case 2: OP(2, ##__VA_ARGS__) case 3: OP(3, ##__VA_ARGS__)   \
+    case 4: OP(4, ##__VA_ARGS__) case 5: OP(5, ##__VA_ARGS__) case 6: OP(6, ##__VA_ARGS__) default: OP(7, ##__VA_ARGS__)  \
+  }
+  // one k-step (4 columns) at a time: the A fragments of the step, then its DMMAs (14 independent accumulators between two
+  // DMMAs on the same one); 16 warps per SM (two CTAs) cover the load-to-use latency
   for (int k0 = 0; k0 < K4; k0 += 4) {
-    const double b0 = Bt[r * ldb + k0 + c], b1 = Bt[(8 + r) * ldb + k0 + c];
-#pragma unroll
-    for (int i = 0; i < MAXF; ++i) {
-      if (i >= mf) break;
-      if (tri && k0 > 8 * i + 7 && i != dense_frag) continue;     // above the diagonal of L_A^-1 (warp-uniform)
-      const double a = A[(8 * i + r) * lda + k0 + c];
-      dmma884(acc[i][0][0], acc[i][0][1], a, b0);
-      dmma884(acc[i][1][0], acc[i][1][1], a, b1);
-    }
+    const int imin = tri ? k0 >> 3 : 0, first = imin < MF - 1 ? imin : MF - 1;
+    const double b0 = B0[k0], b1 = B1[k0];
+    double av[8];
+    B7_FRAG_SWITCH(B7_FRAG_LOAD, k0)
+    B7_FRAG_SWITCH(B7_FRAG_MMA, b0, b1)
+  }
+#undef B7_FRAG_LOAD
+#undef B7_FRAG_MMA
+#undef B7_FRAG_SWITCH
+}
+
+__device__ __forceinline__ void tile_mma(const double* __restrict__ A, int lda, int mf, int K4, const double* __restrict__ Bt, int ldb,
+                                         int lane, double (&acc)[MAXF][2][2], bool tri) {
+  switch (mf) {
+    case 1: tile_mma_t<1>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 2: tile_mma_t<2>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 3: tile_mma_t<3>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 4: tile_mma_t<4>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 5: tile_mma_t<5>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 6: tile_mma_t<6>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 7: tile_mma_t<7>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    default: tile_mma_t<8>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
   }
 }
 
@@ -97,16 +133,39 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
   __syncthreads();
 
   const long long n_tiles = (M + TC - 1) / TC;
-  const int w_in = pl.width[0], lda = pl.act_ld;
+  const int w_in = pl.width[0], lda = pl.act_ld, w4 = (w_in + 3) / 4 * 4, padw = w4 - w_in;
+  double* cur = sh + pl.act_off;
+  const int dq = THREADS / w_in, dr = THREADS % w_in, cc0 = tid / w_in, kk0 = tid % w_in;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long c0 = tile * TC;
     const int nc = (int)min((long long)TC, M - c0);
-    double* cur = sh + pl.act_off;
-    // ---- input tile: nc x w_in contiguous doubles -> [cand][lda], zero padded to a multiple of 4 columns ----
-    const int w4 = (w_in + 3) / 4 * 4;
-    for (int e = tid; e < TC * w4; e += THREADS) {
-      const int cc = e / w4, k = e % w4;
-      cur[cc * lda + k] = (cc < nc && k < w_in) ? in[(c0 + cc) * w_in + k] : 0.0;
+    // ---- input tile: nc x w_in contiguous doubles -> [cand][lda].  All of a thread's global loads are issued before the
+    // first shared-memory store (a loop of load / store pairs was latency bound, ~5 us per tile); the second CTA of the SM
+    // computes meanwhile.  Zero padding: columns w_in .. w4-1 (a wider layer output of the previous tile may have used
+    // them) and rows >= nc ----
+    {
+      constexpr int NLD = 16;                          // loads in flight per thread; two rounds cover widths <= 64
+      const double* src = in + c0 * w_in;
+      const int total = nc * w_in;
+      int cc = cc0, k = kk0;
+#pragma unroll 1
+      for (int round = 0; round < TC * 64 / THREADS / NLD; ++round) {
+        const int f0 = tid + round * NLD * THREADS;
+        if (round * NLD * THREADS >= TC * w_in) break;
+        double buf[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+          const int f = f0 + i * THREADS;
+          buf[i] = f < total ? src[f] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+          if (f0 + i * THREADS < TC * w_in) cur[cc * lda + k] = buf[i];     // rows >= nc receive the zeros loaded above
+          cc += dq; k += dr;
+          if (k >= w_in) { k -= w_in; ++cc; }
+        }
+      }
+      for (int e = tid; e < TC * padw; e += THREADS) cur[(e / padw) * lda + w_in + e % padw] = 0.0;
     }
     __syncthreads();
     // ---- MLP layers ----
@@ -115,7 +174,7 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
       double acc[MAXF][2][2];
 #pragma unroll
       for (int i = 0; i < MAXF; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-      tile_mma(sh + pl.w_off[l], ld_of(hi), mf, K4, cur + warp * 16 * lda, lda, lane, acc, false, -1);
+      tile_mma(sh + pl.w_off[l], ld_of(hi), mf, K4, cur + warp * 16 * lda, lda, lane, acc, false);
       const double* bias = sh + pl.b_off[l];
       const int ho4 = (ho + 3) / 4 * 4;
       __syncwarp();                                    // every lane has read the warp's 16 input rows: overwrite them in place
@@ -143,12 +202,12 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
       for (int e = tid; e < nc * w_last; e += THREADS) feat_out[c0 * w_last + e] = cur[(e / w_last) * lda + e % w_last];
     } else {
       // ---- BLR head per draw: rows 0 .. D-1 of the product are v = L_A^-1 phi, row D is w^T phi ----
-      const int mf = pl.head_rows / 8, K4 = (D + 3) / 4 * 4, dense = D / 8;
+      const int mf = pl.head_rows / 8, K4 = (D + 3) / 4 * 4;      // the dense row w^T sits in the last fragment (D / 8 = mf - 1)
       for (int s = 0; s < pl.S; ++s) {
         double acc[MAXF][2][2];
 #pragma unroll
         for (int i = 0; i < MAXF; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-        tile_mma(sh + pl.head_off + s * pl.head_rows * ldh, ldh, mf, K4, cur + warp * 16 * lda, lda, lane, acc, true, dense);
+        tile_mma(sh + pl.head_off + s * pl.head_rows * ldh, ldh, mf, K4, cur + warp * 16 * lda, lda, lane, acc, true);
         double s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, mu[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int i = 0; i < MAXF; ++i) {
@@ -225,14 +284,14 @@ int b7_launch_dngo_tiles(b7_ctx* ctx, const double* in, int64_t M, int n_layers,
   pl.act_ld = ld_of(wmax);
   pl.act_off = off; off += TC * pl.act_ld;
   const size_t smem = (size_t)off * sizeof(double);
-  if (smem > 200 * 1024) return 1;
+  if (smem > 226 * 1024) return 1;
   static bool done[16] = {false};
   if (!done[ctx->device & 15]) {
-    B7_CUDA(cudaFuncSetAttribute(dngo_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B7_CUDA(cudaFuncSetAttribute(dngo_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     done[ctx->device & 15] = true;
   }
   const int64_t n_tiles = (M + TC - 1) / TC;
-  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * per_sm);
   dngo_tile_kernel<<<grid, THREADS, smem, ctx->stream>>>(in, M, pl, pt, Linv, w, par, D, ld_out, mean, var, feat_out);
   b7_count(ctx);

@@ -92,8 +92,8 @@ struct b7_comm {
   std::vector<b7_ctx*> ctx;          // one per local device
   std::vector<ncclComm_t> nccl;      // one per local device (empty when world == 1)
   std::vector<double*> triple;       // per local device: world x 3 doubles (best, index, nan) for the combine
-  std::vector<double*> meta;         // per local device: device scratch for (info, logml, jitter) per draw
-  size_t meta_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // exchange timing on the first local device (the context's own timer events
+                                              // belong to the caller's b7_timer_begin / b7_timer_end)
   int n_local() const { return (int)ctx.size(); }
 };
 
@@ -151,8 +151,10 @@ int comm_finish_init(b7_comm* c) {
     double* t = nullptr;
     B7_CHECK(b7_pool_alloc(c->ctx[i], (void**)&t, sizeof(double) * 3 * (size_t)c->world));
     c->triple.push_back(t);
-    c->meta.push_back(nullptr);
   }
+  B7_CUDA(cudaSetDevice(c->ctx[0]->device));
+  B7_CUDA(cudaEventCreate(&c->ev0));
+  B7_CUDA(cudaEventCreate(&c->ev1));
   return 0;
 }
 
@@ -239,8 +241,10 @@ void b7_comm_free(b7_comm* c) {
     cudaSetDevice(c->ctx[i]->device);
     cudaStreamSynchronize(c->ctx[i]->stream);
     if (i < c->triple.size()) b7_pool_free(c->ctx[i], c->triple[i]);
-    if (i < c->meta.size()) b7_pool_free(c->ctx[i], c->meta[i]);
   }
+  if (!c->ctx.empty()) cudaSetDevice(c->ctx[0]->device);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
   for (ncclComm_t n : c->nccl)
     if (n) g_nccl.CommDestroy(n);
   if (c->owns_ctx)
@@ -359,20 +363,20 @@ int b7_gp_fit_sharded(b7_comm* c, int kernel, const double* X, const double* y, 
   }
   b7_ctx* x0 = c->ctx[0];
   cudaSetDevice(x0->device);
-  if (gather_ms) cudaEventRecord(x0->tm0, x0->stream);
+  if (gather_ms) cudaEventRecord(c->ev0, x0->stream);
   if ((rc = gather_draws(c, b0, i8 ? b7_i8_facs_stride((int)Np) : Np * Np * sizeof(double), S)) < 0) return fail(rc);
   if ((rc = gather_draws(c, b1, Np * sizeof(double), S)) < 0) return fail(rc);
   if ((rc = gather_draws(c, b2, Np * sizeof(double), S)) < 0) return fail(rc);
   if ((rc = gather_draws(c, bm, 3 * sizeof(double), S)) < 0) return fail(rc);
   cudaSetDevice(x0->device);
-  if (gather_ms) cudaEventRecord(x0->tm1, x0->stream);
+  if (gather_ms) cudaEventRecord(c->ev1, x0->stream);
   // 3. bookkeeping on every handle
   rc = for_each_local(c, [&](int i) { return b7_gp_finish_gather(out[i], i8); });
   if (rc < 0) return fail(rc);
   if (gather_ms) {
     float ms = 0;
     cudaSetDevice(x0->device);
-    if (cudaEventElapsedTime(&ms, x0->tm0, x0->tm1) == cudaSuccess) *gather_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) *gather_ms = ms;
   }
   for (int s = 0; s < S; ++s) {
     if (info) info[s] = out[0]->info_host[s];

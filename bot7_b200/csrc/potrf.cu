@@ -480,7 +480,10 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   // at N = 4096: S = 32 26.7 -> 17.7 ms, S = 1 4.1 -> 4.8 ms)
   // refit latency, ms, int8 / fp64 updates: N = 4096 S = 4 5.7 / 5.9, S = 8 7.4 / 8.8, S = 16 11.2 / 15.3;
   // N = 2048 S = 4 2.5 / 2.25, S = 16 3.5 / 3.5, S = 32 4.3 / 4.8 -> needs count * NB^2 >= 4096
-  const bool i8 = ctx->use_i8 && ctx->potrf_i8 && count >= 4 && (long long)count * NB * NB >= 4096 && NB > W && Np <= B7_I8_MAX_NP;
+  // The choice looks at the handle's total number of draws, not at how many of them this call factorises: a sharded fit
+  // (each GPU factorises S / G draws) then uses the same arithmetic as the one-GPU fit and stays bit-identical to it.
+  const int batch = gp->S;
+  const bool i8 = ctx->use_i8 && ctx->potrf_i8 && batch >= 4 && (long long)batch * NB * NB >= 4096 && NB > W && Np <= B7_I8_MAX_NP;
   int8_t* pS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   double* pSig[2] = {nullptr, nullptr};
   const size_t p_stride = i8 ? b7_i8_panel_bytes(Np, W) : 0;
