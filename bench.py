@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=None, help="override the config's candidate count (per GPU if weak, total if strong)")
     ap.add_argument("--e2e-candidates", type=int, default=None, help="candidates per GPU of the end-to-end leg (default: the step's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-path", action="store_true", help="skip the FP64 DMMA path that the 1-GPU headline run times beside the default one")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -417,7 +418,7 @@ def main():
     other_path = L.PATH_FP64_DMMA if default_path == L.PATH_INT8_OZAKI else L.PATH_INT8_OZAKI
     path_name = {L.PATH_FP64_DMMA: "fp64_dmma", L.PATH_INT8_OZAKI: "int8_ozaki"}
     other = None
-    if world == 1 and args.config == "headline":
+    if world == 1 and args.config == "headline" and not args.no_other_path:
         # secondary path first (so that the default path is the one left selected), then the default path = `value`
         o_ms, _, o_launches, _, o_clk, o_res = timed(other_path, 2, args.steps, False)
         _, _, _, o_st, _, _ = timed(other_path, 0, 1, True)
