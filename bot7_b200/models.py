@@ -130,6 +130,10 @@ class gp_regressor:
         c.setdefault("nSamples", 1)
         c.setdefault("burnin", 0)
         c.setdefault("prior_std", 2.0)     # declared: independent N(0, prior_std^2) on every hyp entry
+        # declared initial state of the chain (bots/abstract.lua:148 model:init; gpTorch7's own values are unknown)
+        c.setdefault("init_lengthscale", 0.5)
+        c.setdefault("init_sigma_f", 1.0)
+        c.setdefault("init_noise", None)   # sigma_n^2; None: 1e-2, or 1e-6 with `noiseless`
         c.setdefault("speculative", True)  # batched density evaluations; the chain is identical either way
         c.setdefault("spec_width", 8)     # profiles/refit_vs_width_r01.json: 8 evaluations cost 1.0-2.1x one
         self.config = c
@@ -153,9 +157,12 @@ class gp_regressor:
         X = np.atleast_2d(L.as_f64(X))
         d = X.shape[1]
         h = np.zeros(d + 3)
-        h[:d] = math.log(0.5)
-        h[d] = 0.0
-        h[d + 1] = 0.5 * math.log(1e-6 if self.config["noiseless"] else 1e-2)
+        noise = self.config["init_noise"]
+        if noise is None:
+            noise = 1e-6 if self.config["noiseless"] else 1e-2
+        h[:d] = math.log(self.config["init_lengthscale"])
+        h[d] = math.log(self.config["init_sigma_f"])
+        h[d + 1] = 0.5 * math.log(noise)
         h[d + 2] = float(np.mean(Y))
         self.hyp = h
         return self

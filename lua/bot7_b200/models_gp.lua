@@ -24,6 +24,9 @@ function model:__init(config)
   config['nSamples']   = config.nSamples  or 1
   config['prior_std']  = config.prior_std or 2.0     -- declared: independent N(0, prior_std^2) on every hyp entry
   config['spec_width'] = config.spec_width or 8      -- density evaluations per batched device call
+  -- declared initial state of the chain (model:init); gpTorch7's own values are unknown
+  config['init_lengthscale'] = config.init_lengthscale or 0.5
+  config['init_sigma_f']     = config.init_sigma_f or 1.0
   self.config = config
   self.hyp    = nil
 end
@@ -38,9 +41,9 @@ end
 function model:init(X, Y)
   local d = X:size(2)
   local h = torch.zeros(1, d + 3)
-  h:narrow(2, 1, d):fill(math.log(0.5))
-  h[1][d + 1] = 0.0
-  h[1][d + 2] = 0.5 * math.log(self.config.noiseless and 1e-6 or 1e-2)
+  h:narrow(2, 1, d):fill(math.log(self.config.init_lengthscale))
+  h[1][d + 1] = math.log(self.config.init_sigma_f)
+  h[1][d + 2] = 0.5 * math.log(self.config.init_noise or (self.config.noiseless and 1e-6 or 1e-2))
   h[1][d + 3] = Y:mean()
   self.hyp = h
   return self
