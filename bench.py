@@ -219,7 +219,7 @@ def run_reference(args, cfg, rank):
         return
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_sample(cfg, n_draws=1)
+        last = cpu_sample(cfg, n_draws=1, m_cand=32768)     # ~5 s of CPU work per step: K + W steps end within a few minutes
         if i >= args.warmup:
             vals.append(last["value"])
     value = statistics.mean(vals)
@@ -612,17 +612,20 @@ def bench_dngo(args, cfg, comm, ctx, L, lib, models, parallel, dist, pk, Xo, y, 
     for i in range(5):
         barrier()
         t0 = time.perf_counter()
-        f2 = models.mlp_features(grid, Ws, bs, True, ctx)
         Z0_ = np.maximum(Xo @ W + b, 0.0)
         b2 = models.BLRFactors(Z0_, y, hyp, ctx)
-        sc = np.empty(cnt)
-        am, amo, best, nn = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
-        L.check(lib.b7_blr_score(b2.handle, f2.handle, EI, 0.0, 0, -1.0, fmin, L.dptr(sc), C.byref(am), C.byref(amo), C.byref(best), C.byref(nn)))
+        # dngo:predict + score + argmax in one pass over the device grid: the basis is evaluated in front of the head,
+        # the 1.7 GB feature matrix Z1 is never stored (b7_dngo_score)
+        sc, am_, amo_, best_, nn_ = models.dngo_score(b2, grid, Ws, bs, True, EI, 0.0, 0, -1.0, fmin, want_scores=True)
         if dist:
-            parallel.allgather_argmax(best.value, amo.value + row0, nn.value)
+            parallel.allgather_argmax(best_, amo_ + row0, nn_)
         e2e_times.append(time.perf_counter() - t0)
         b2.free()
-        f2.free()
+    ctx.set_profiling(True)
+    ctx.reset_timers()
+    models.dngo_score(blr, grid, Ws, bs, True, EI, 0.0, 0, -1.0, fmin)
+    fused_ms = ctx.stage_times()["blr"][0]
+    ctx.set_profiling(False)
     e2e_s = allmax(float(np.median(e2e_times[2:])))[0]
     if rank != 0:
         if dist:
@@ -638,8 +641,9 @@ def bench_dngo(args, cfg, comm, ctx, L, lib, models, parallel, dist, pk, Xo, y, 
                    "parallelism": f"candidate-sharded x{world} (no data-path collective; triples combined over gloo)"},
         "e2e": {"value": world * cnt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(Xo.nbytes + y.nbytes + Z0.nbytes + hyp.nbytes),
                 "d2h_bytes_per_step": int(cnt * 8 + 32),
-                "includes": "b7_mlp_features over the device Sobol grid + host basis of the observations + b7_blr_fit + b7_blr_score with the "
-                            "score vector copied back; median of 3 steps after 2 untimed ones", "seconds_per_step": e2e_s},
+                "includes": "host basis of the observations + b7_blr_fit + b7_dngo_score (basis + BLR head + EI + argmax in one pass over the "
+                            "device Sobol grid, Z1 never stored) with the score vector copied back; median of 3 steps after 2 untimed ones",
+                "seconds_per_step": e2e_s},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "BLR moments kernel (blr.cu): mean / variance of the BLR head per candidate",
                      "achieved": bytes_alg / (blr_ms * 1e-3) * 1e-9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -648,7 +652,8 @@ def bench_dngo(args, cfg, comm, ctx, L, lib, models, parallel, dist, pk, Xo, y, 
                      "fp64_tflops": cnt * (D * D + 2 * D) * 2 / (blr_ms * 1e-3) * 1e-12, "fp64_peak_tflops": pk["fp64_dmma_tflops"],
                      "peak_source": pk["hbm_source"]},
         "stages": {"sobol": {"ms": sobol_ms}, "basis_mlp": {"ms": basis_ms, "tflops": cnt * (d * D) * 2 / (basis_ms * 1e-3) * 1e-12 if basis_ms else None},
-                   "blr_fit": {"ms": fit_ms}, "blr_moments": {"ms_per_step": blr_ms}, "score": {"ms_per_step": st["score"][0] / 3}},
+                   "blr_fit": {"ms": fit_ms}, "blr_moments": {"ms_per_step": blr_ms}, "score": {"ms_per_step": st["score"][0] / 3},
+                   "fused_basis_plus_head": {"ms": fused_ms, "note": "b7_dngo_score's tile kernel: basis + head per tile, reads 8 d bytes per candidate"}},
         "peaks": pk, "result": {"best": res[0], "global_index": res[1], "nan_count": res[2]},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -249,7 +249,7 @@ __device__ __forceinline__ void epilogue_row_block(uint32_t tmem, int tid, int w
 }
 
 // The pair kernel's epilogue: 8 warps, warp w drains TMEM lanes 32 (w & 3) .. and the 32 candidate columns of half
-// w >> 2; the 7 class loads go out in batches of 3 + 3 + 1 with one wait per batch (the one-load-one-wait drain of
+// w >> 2; the 7 class loads go out in two batches (3 + 4) with one wait per batch (the one-load-one-wait drain of
 // 4 warps kept the accumulators busy for 2.9 us per row block, 6.6 % of the kernel: ncu pair_r02).  Same fma chain
 // per entry and same summation tree as epilogue_row_block: bit-identical results.
 template <typename F>
@@ -258,27 +258,35 @@ __device__ __forceinline__ void epilogue_row_block8(uint32_t tmem, int tid, int 
   const int q = warp & 3, hc = warp >> 2;
   const uint32_t base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hc * 32);
   double v[32];
-  uint32_t a[3][32];
+  uint32_t a[4][32];
+  // classes 0-2, then classes 3-6: the accumulators are released as soon as the second batch sits in registers, before its
+  // int -> fp64 conversion (4/7 of the FP64 work of the drain leaves the MMA warp's critical path)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tmem_ld32_async(base + (uint32_t)(i * TN), a[i]);
+  tmem_ld_wait();
 #pragma unroll
   for (int c = 0; c < 32; ++c) v[c] = 0.0;
 #pragma unroll
-  for (int b0 = 0; b0 < NS; b0 += 3) {
+  for (int i = 0; i < 3; ++i) {
+    tmem_pin(a[i]);
+    const double wt = ldexp(1.0, 4 - 8 * (i + 2));
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (b0 + i < NS) tmem_ld32_async(base + (uint32_t)((b0 + i) * TN), a[i]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (b0 + i < NS) {
-        tmem_pin(a[i]);
-        const double wt = ldexp(1.0, 4 - 8 * (b0 + i + 2));
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)a[i][c], wt, v[c]);
-      }
+    for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)a[i][c], wt, v[c]);
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tmem_ld32_async(base + (uint32_t)((3 + i) * TN), a[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tmem_pin(a[i]);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) arrive_drained();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double wt = ldexp(1.0, 4 - 8 * (i + 5));
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = fma((double)(int)a[i][c], wt, v[c]);
+  }
 #pragma unroll
   for (int c = 0; c < 32; ++c) { const double vv = v[c] * sc; v[c] = vv * vv; }
   rr[q * TN + hc * 32 + lane] = lane_transpose_sum(v, lane);
