@@ -162,3 +162,34 @@ def test_score_config_defaults():
     assert cb.config["tradeoff"] == 0 and cb.config["bound"] == "lower" and cb.config["sign"] == -1.0
     assert scores.score_args(cb) == (1, 0.0, 0, -1.0)
     assert scores.score_args(scores.confidence_bound({"bound": "upper", "sign": 1.0}))[2:] == (1, 1.0)
+
+
+def test_c_abi_shard_rule_matches_the_host_rule():
+    # b7_shard_range (pure host code in the library: no GPU needed) is the rule that shards candidates AND draws inside
+    # b7_gp_fit_sharded / b7_acq_score_multi; the Python twin and bench.py use parallel.shard_range
+    import ctypes as C
+    from bot7_b200 import _lib as L
+    from bot7_b200 import parallel
+    lib = L.lib()
+    for M in (0, 1, 5, 32, 37888, 2 ** 22 + 3):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for rank in range(world):
+                r0, cnt = C.c_int64(), C.c_int64()
+                assert lib.b7_shard_range(M, world, rank, C.byref(r0), C.byref(cnt)) == 0
+                assert (r0.value, cnt.value) == parallel.shard_range(M, world, rank)
+                assert r0.value == covered
+                covered += cnt.value
+            assert covered == M
+    r0, cnt = C.c_int64(), C.c_int64()
+    assert lib.b7_shard_range(10, 2, 2, C.byref(r0), C.byref(cnt)) < 0          # rank out of range
+
+
+def test_comm_init_fails_loudly_without_gpu():
+    import ctypes as C
+    from bot7_b200 import _lib as L
+    if L.lib().b7_device_count() > 0:
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert L.lib().b7_comm_init_all(2, None, C.byref(h)) < 0
+    assert b"devices" in L.lib().b7_last_error() or b"CUDA" in L.lib().b7_last_error()
