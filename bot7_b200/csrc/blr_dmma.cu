@@ -12,6 +12,10 @@
 // above the diagonal of the triangular L_A^-1.  The one-DFMA-thread-per-candidate kernels of blr.cu ran at 27 %
 // (BLR) and 22 % (MLP) of the FP64 pipe; they remain as the fallback for shapes whose weights do not fit.
 // With the basis fused, the 8 D bytes per candidate of Z1 (1.7 GB at config 4) are never written or read.
+// A tile's rows are contiguous in the grid, so the input tile arrives as ONE cp.async.bulk (TMA unit, mbarrier-tracked) in
+// its raw layout [candidate][w_in]; the fragment loads read it with that leading dimension (2-way bank conflicts on the two
+// B loads of a k-step at most) and mask the columns beyond w_in, so nothing is repacked: the first versions spent ~400 of
+// their ~2 700 instructions per warp and tile on staging the tile through registers.
 #include <algorithm>
 #include <vector>
 
@@ -41,8 +45,10 @@ struct Plan {
   int b_off[MAXL];
   int head_off;                 // [S][rows_pad][ld(D)] head matrices
   int head_rows;                // D + 1 rounded up to 8
-  int act_off;                  // activation buffer [TC][act_ld]; a layer overwrites it in place (a warp owns its 16 rows)
+  int raw_off;                  // input tile in its global layout [TC][width[0]] (one bulk copy)
+  int act_off;                  // activation buffer [TC][act_ld] (only with layers); a layer >= 1 overwrites it in place
   int act_ld;
+  int bar_off;                  // mbarrier of the bulk copy
   int S;                        // draws staged (0: no head, write the features)
 };
 
@@ -52,55 +58,86 @@ struct Ptrs {
 };
 
 // acc[i][j] (+)= A[8i.., k] * B[cand.., k]^T over k < K4; A: rows x lda, Bt: [cand][ldb].
-// MF (output fragments) is a compile-time constant so that the fragment loop carries no branches: the loads of a pair of
-// k-steps (up to 2 x 7 A fragments + 4 B fragments) are issued together in front of their up to 28 DMMAs (with a runtime
-// bound and `break` in the loop every fragment load sat in front of its own two DMMAs: 28 % of the DMMA issue rate).
+// MF (output fragments) and LDA (leading dimension of A) are compile-time constants: the fragment loop carries no branches
+// and every A fragment is one LDS at a constant offset from one running pointer (with run-time shapes the compiler spent ~20
+// integer instructions per fragment load on re-deriving addresses: 2 700 instructions per warp and tile, 4 % of them DMMAs).
 // tri: A is [L^-1 ; w^T] -- fragment i is zero for k > 8 i + 7, except the last one (it holds the dense row w^T), so the
 // fragments active at k0 are the suffix i >= k0 / 8.
-template <int MF>
-__device__ __forceinline__ void tile_mma_t(const double* __restrict__ A, int lda, int K4, const double* __restrict__ Bt, int ldb, int lane,
+template <int MF, int LDA>
+__device__ __forceinline__ void tile_mma_t(const double* __restrict__ A, int K4, const double* __restrict__ Bt, int ldb, int kmax, int lane,
                                            double (&acc)[MAXF][2][2], bool tri) {
   const int r = lane >> 2, c = lane & 3;
-  const double* Ar = A + r * lda + c;
   const double* B0 = Bt + r * ldb + c;
   const double* B1 = Bt + (8 + r) * ldb + c;
-  // Fragments i >= first are active at this pair of k-steps.  The skip is a real (warp-uniform) jump into a fall-through
-  // switch: a predicated-off DMMA still holds the FP64 tensor pipe for its 16 cycles (ncu dngo_r02: 47.7 M DMMAs issued,
-  // 28.8 M predicated on, pipe busy for all of them).
-#define B7_FRAG_LOAD(I, KK)                                                  \
-  if (MF > I) { av[I] = Ar[8 * I * lda + KK]; }
-#define B7_FRAG_MMA(I, BA, BB)                                               \
-  if (MF > I) { dmma884(acc[I][0][0], acc[I][0][1], av[I], BA); dmma884(acc[I][1][0], acc[I][1][1], av[I], BB); }
-#define B7_FRAG_SWITCH(OP, ...)                                              \
-  switch (first) {                                                           \
-    case 0: OP(0, ##__VA_ARGS__) case 1: OP(1, ##__VA_ARGS__) case 2: OP(2, ##__VA_ARGS__) case 3: OP(3, ##__VA_ARGS__)   \
-    case 4: OP(4, ##__VA_ARGS__) case 5: OP(5, ##__VA_ARGS__) case 6: OP(6, ##__VA_ARGS__) default: OP(7, ##__VA_ARGS__)  \
+  const double* Ar = A + r * LDA + c;                  // LDA is a compile-time constant: fragment i is one LDS at [Ar + k0 + 8 i LDA]
+  // A predicated-off DMMA still holds the FP64 tensor pipe for its 16 cycles (ncu dngo_r02: 47.7 M DMMAs issued, 28.8 M
+  // predicated on, pipe busy for all of them): fragments above the diagonal are skipped at compile time, not by predicates.
+  if (tri) {
+    // [L^-1 ; w^T]: fragments i >= q (and the last one) are non-zero in columns 8 q .. 8 q + 7.  q is unrolled at compile
+    // time, so every fragment load is one LDS at a constant offset and the skip costs nothing at run time.
+#pragma unroll
+    for (int q = 0; q < MF; ++q) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k0 = 8 * q + 4 * h;
+        if (k0 < K4) {                                   // warp-uniform
+          const bool kin = k0 + c < kmax;
+          const double b0 = kin ? B0[k0] : 0.0, b1 = kin ? B1[k0] : 0.0;
+          double av[8];
+#pragma unroll
+          for (int i = 0; i < MF; ++i)
+            if (i >= q || i == MF - 1) av[i] = Ar[8 * i * LDA + k0];
+#pragma unroll
+          for (int i = 0; i < MF; ++i)
+            if (i >= q || i == MF - 1) {
+              dmma884(acc[i][0][0], acc[i][0][1], av[i], b0);
+              dmma884(acc[i][1][0], acc[i][1][1], av[i], b1);
+            }
+        }
+      }
+    }
+    return;
   }
-  // one k-step (4 columns) at a time: the A fragments of the step, then its DMMAs (14 independent accumulators between two
-  // DMMAs on the same one); 16 warps per SM (two CTAs) cover the load-to-use latency
-  for (int k0 = 0; k0 < K4; k0 += 4) {
-    const int imin = tri ? k0 >> 3 : 0, first = imin < MF - 1 ? imin : MF - 1;
-    const double b0 = B0[k0], b1 = B1[k0];
+  // dense layers: one k-step (4 columns) at a time, the A fragments of the step, then its DMMAs (up to 14 independent
+  // accumulators between two DMMAs on the same one; dmma884 is `asm volatile`, kept in program order)
+  for (int k0 = 0; k0 < K4; k0 += 4, Ar += 4, B0 += 4, B1 += 4) {
+    const bool kin = k0 + c < kmax;                    // the raw tile has no padding columns: mask instead
+    const double b0 = kin ? *B0 : 0.0, b1 = kin ? *B1 : 0.0;
     double av[8];
-    B7_FRAG_SWITCH(B7_FRAG_LOAD, k0)
-    B7_FRAG_SWITCH(B7_FRAG_MMA, b0, b1)
+#pragma unroll
+    for (int i = 0; i < MF; ++i) av[i] = Ar[8 * i * LDA];
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      dmma884(acc[i][0][0], acc[i][0][1], av[i], b0);
+      dmma884(acc[i][1][0], acc[i][1][1], av[i], b1);
+    }
   }
-#undef B7_FRAG_LOAD
-#undef B7_FRAG_MMA
-#undef B7_FRAG_SWITCH
 }
 
-__device__ __forceinline__ void tile_mma(const double* __restrict__ A, int lda, int mf, int K4, const double* __restrict__ Bt, int ldb,
-                                         int lane, double (&acc)[MAXF][2][2], bool tri) {
+template <int LDA>
+__device__ __forceinline__ void tile_mma_l(const double* __restrict__ A, int mf, int K4, const double* __restrict__ Bt, int ldb, int kmax,
+                                           int lane, double (&acc)[MAXF][2][2], bool tri) {
   switch (mf) {
-    case 1: tile_mma_t<1>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 2: tile_mma_t<2>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 3: tile_mma_t<3>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 4: tile_mma_t<4>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 5: tile_mma_t<5>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 6: tile_mma_t<6>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    case 7: tile_mma_t<7>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
-    default: tile_mma_t<8>(A, lda, K4, Bt, ldb, lane, acc, tri); break;
+    case 1: tile_mma_t<1, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 2: tile_mma_t<2, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 3: tile_mma_t<3, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 4: tile_mma_t<4, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 5: tile_mma_t<5, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 6: tile_mma_t<6, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 7: tile_mma_t<7, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    default: tile_mma_t<8, LDA>(A, K4, Bt, ldb, kmax, lane, acc, tri); break;
+  }
+}
+
+// lda is ld_of(k width): one of 4, 20, 36, 52, 68
+__device__ __forceinline__ void tile_mma(const double* __restrict__ A, int lda, int mf, int K4, const double* __restrict__ Bt, int ldb,
+                                         int kmax, int lane, double (&acc)[MAXF][2][2], bool tri) {
+  switch (lda) {
+    case 4: tile_mma_l<4>(A, mf, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 20: tile_mma_l<20>(A, mf, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 36: tile_mma_l<36>(A, mf, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    case 52: tile_mma_l<52>(A, mf, K4, Bt, ldb, kmax, lane, acc, tri); break;
+    default: tile_mma_l<68>(A, mf, K4, Bt, ldb, kmax, lane, acc, tri); break;
   }
 }
 
@@ -133,73 +170,87 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
   __syncthreads();
 
   const long long n_tiles = (M + TC - 1) / TC;
-  const int w_in = pl.width[0], lda = pl.act_ld, w4 = (w_in + 3) / 4 * 4, padw = w4 - w_in;
-  double* cur = sh + pl.act_off;
-  const int dq = THREADS / w_in, dr = THREADS % w_in, cc0 = tid / w_in, kk0 = tid % w_in;
+  const int w_in = pl.width[0], lda = pl.act_ld;
+  double* raw = sh + pl.raw_off;
+  double* act = sh + pl.act_off;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sh + pl.bar_off);
+  // the tile is one contiguous run of nc * w_in doubles: a single bulk copy when rows are a multiple of 16 bytes
+  const bool bulk = (w_in & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  auto issue = [&](long long tile) {                   // thread 0 only
+    const long long c0 = tile * TC;
+    const unsigned bytes = (unsigned)(min((long long)TC, M - c0) * w_in * 8);
+    b7g::mbar_arrive_expect_tx(bar, bytes);
+    b7g::bulk_g2s(raw, in + c0 * w_in, bytes, bar);
+  };
+  if (tid == 0) {
+    b7g::mbar_init(bar, 1);
+    b7g::mbar_fence_init();
+    if (bulk && (long long)blockIdx.x < n_tiles) issue(blockIdx.x);
+  }
+  __syncthreads();
+  unsigned phase = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long c0 = tile * TC;
     const int nc = (int)min((long long)TC, M - c0);
-    // ---- input tile: nc x w_in contiguous doubles -> [cand][lda].  All of a thread's global loads are issued before the
-    // first shared-memory store (a loop of load / store pairs was latency bound, ~5 us per tile); the second CTA of the SM
-    // computes meanwhile.  Zero padding: columns w_in .. w4-1 (a wider layer output of the previous tile may have used
-    // them) and rows >= nc ----
-    {
-      constexpr int NLD = 16;                          // loads in flight per thread; two rounds cover widths <= 64
+    const bool more = tile + gridDim.x < n_tiles;
+    if (bulk) {
+      b7g::mbar_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      // rows that are not a multiple of 16 bytes: flat coalesced copy into the same raw layout, 16 loads in flight per thread
       const double* src = in + c0 * w_in;
       const int total = nc * w_in;
-      int cc = cc0, k = kk0;
-#pragma unroll 1
-      for (int round = 0; round < TC * 64 / THREADS / NLD; ++round) {
-        const int f0 = tid + round * NLD * THREADS;
-        if (round * NLD * THREADS >= TC * w_in) break;
-        double buf[NLD];
+      for (int f0 = tid; f0 < total; f0 += 16 * THREADS) {
+        double buf[16];
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-          const int f = f0 + i * THREADS;
-          buf[i] = f < total ? src[f] : 0.0;
-        }
+        for (int i = 0; i < 16; ++i) buf[i] = f0 + i * THREADS < total ? src[f0 + i * THREADS] : 0.0;
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-          if (f0 + i * THREADS < TC * w_in) cur[cc * lda + k] = buf[i];     // rows >= nc receive the zeros loaded above
-          cc += dq; k += dr;
-          if (k >= w_in) { k -= w_in; ++cc; }
-        }
+        for (int i = 0; i < 16; ++i)
+          if (f0 + i * THREADS < total) raw[f0 + i * THREADS] = buf[i];
       }
-      for (int e = tid; e < TC * padw; e += THREADS) cur[(e / padw) * lda + w_in + e % padw] = 0.0;
+      __syncthreads();
     }
-    __syncthreads();
+    // rows >= nc of a partial last tile hold whatever the previous tile left: their results are never stored
+    const double* X = raw + warp * 16 * w_in;          // this warp's 16 candidates
+    int ldx = w_in;
     // ---- MLP layers ----
     for (int l = 0; l < pl.n_layers; ++l) {
       const int hi = pl.width[l], ho = pl.width[l + 1], mf = (ho + 7) / 8, K4 = (hi + 3) / 4 * 4;
       double acc[MAXF][2][2];
 #pragma unroll
       for (int i = 0; i < MAXF; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-      tile_mma(sh + pl.w_off[l], ld_of(hi), mf, K4, cur + warp * 16 * lda, lda, lane, acc, false);
+      tile_mma(sh + pl.w_off[l], ld_of(hi), mf, K4, X, ldx, hi, lane, acc, false);
+      if (l == 0 && bulk) {                            // every warp is done with the raw tile: fetch the next one under the rest
+        __syncthreads();
+        if (tid == 0 && more) issue(tile + gridDim.x);
+      }
       const double* bias = sh + pl.b_off[l];
-      const int ho4 = (ho + 3) / 4 * 4;
       __syncwarp();                                    // every lane has read the warp's 16 input rows: overwrite them in place
+      double* out = act + warp * 16 * lda;
 #pragma unroll
       for (int i = 0; i < MAXF; ++i) {
         if (i >= mf) break;
         const int row = 8 * i + r;
-        if (row >= ho4) continue;                      // columns ho .. ho4-1 must be written (zeros) for the next K loop
+        if (row >= ho) continue;
         const double bb = bias[row];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            double v = row < ho ? acc[i][j][e] + bb : 0.0;
+            double v = acc[i][j][e] + bb;
             if (pl.relu[l]) v = v > 0.0 ? v : 0.0;
-            cur[(warp * 16 + 8 * j + 2 * c + e) * lda + row] = v;
+            out[(8 * j + 2 * c + e) * lda + row] = v;
           }
       }
       __syncwarp();                                    // a warp only reads the 16 candidates it wrote
+      X = out;
+      ldx = lda;
     }
     const int w_last = pl.width[pl.n_layers];
     if (pl.S == 0) {
       // ---- features out (b7_mlp_features): [cand][w_last] contiguous ----
       __syncthreads();
-      for (int e = tid; e < nc * w_last; e += THREADS) feat_out[c0 * w_last + e] = cur[(e / w_last) * lda + e % w_last];
+      for (int e = tid; e < nc * w_last; e += THREADS) feat_out[c0 * w_last + e] = act[(e / w_last) * lda + e % w_last];
     } else {
       // ---- BLR head per draw: rows 0 .. D-1 of the product are v = L_A^-1 phi, row D is w^T phi ----
       const int mf = pl.head_rows / 8, K4 = (D + 3) / 4 * 4;      // the dense row w^T sits in the last fragment (D / 8 = mf - 1)
@@ -207,7 +258,11 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
         double acc[MAXF][2][2];
 #pragma unroll
         for (int i = 0; i < MAXF; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-        tile_mma(sh + pl.head_off + s * pl.head_rows * ldh, ldh, mf, K4, cur + warp * 16 * lda, lda, lane, acc, true);
+        tile_mma(sh + pl.head_off + s * pl.head_rows * ldh, ldh, mf, K4, X, ldx, D, lane, acc, true);
+        if (pl.n_layers == 0 && bulk && s == pl.S - 1) {   // head only: the raw tile is free after the last draw's products
+          __syncthreads();
+          if (tid == 0 && more) issue(tile + gridDim.x);
+        }
         double s2[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, mu[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int i = 0; i < MAXF; ++i) {
@@ -247,7 +302,7 @@ dngo_tile_kernel(const double* __restrict__ in, long long M, Plan pl, Ptrs pt, c
         }
       }
     }
-    __syncthreads();                                   // the activation buffers are refilled by the next tile
+    __syncthreads();                                   // raw / act are rewritten by the next tile
   }
 }
 
@@ -282,7 +337,11 @@ int b7_launch_dngo_tiles(b7_ctx* ctx, const double* in, int64_t M, int n_layers,
   pl.head_rows = S > 0 ? (D + 1 + 7) / 8 * 8 : 0;
   pl.head_off = off; off += S * pl.head_rows * (S > 0 ? ld_of(D) : 0);
   pl.act_ld = ld_of(wmax);
-  pl.act_off = off; off += TC * pl.act_ld;
+  off = (off + 1) / 2 * 2;                             // 16-byte aligned destination of the bulk copy
+  pl.raw_off = off; off += TC * dims[0];
+  off = (off + 1) / 2 * 2;
+  pl.act_off = off; off += n_layers > 0 ? TC * pl.act_ld : 0;
+  pl.bar_off = off; off += 2;
   const size_t smem = (size_t)off * sizeof(double);
   if (smem > 226 * 1024) return 1;
   static bool done[16] = {false};
