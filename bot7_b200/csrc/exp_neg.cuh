@@ -42,5 +42,34 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
   return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
 }
 
+// The same function with its six non-trivial constants held in registers (made opaque once per kernel) and the range
+// check as a select at the end.  As written above, the compiler re-materialises every 64-bit constant in front of its DFMA
+// (two moves each) and wraps the call in BSSY / BRA / BSYNC: 16 + 5 of the 85 instructions per K* entry of
+// cov_slices_kernel, which is issue-bound (ncu covslices_r02: FP64 pipe 32 % active, issue slots 71 % busy).  Same FP64
+// operations in the same order: bit-identical results for every argument.
+struct ExpNegK {
+  double l2e, ln2h, ln2l, c5, c4, c3;
+  __device__ __forceinline__ void init() {
+    l2e = 92.33248261689366; ln2h = -0.010830424696249145; ln2l = -(3.623510646634843e-19);
+    c5 = 8.33333333333333322e-03; c4 = 4.16666666666666644e-02; c3 = 1.66666666666666657e-01;
+    asm volatile("" : "+d"(l2e), "+d"(ln2h), "+d"(ln2l), "+d"(c5), "+d"(c4), "+d"(c3));
+  }
+};
+
+__device__ __forceinline__ double exp_neg_k(double x, const double* __restrict__ tab, const ExpNegK& K) {
+  const double t = fma(x, K.l2e, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, K.ln2h, x);
+  r = fma(nf, K.ln2l, r);
+  double p = fma(r, K.c5, K.c4);
+  p = fma(p, r, K.c3);
+  p = fma(p, r, 0.5);
+  p = fma(p * r, r, r);
+  const double T = tab[n & 63];
+  const double v = fma(T, p, T);
+  const double res = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+  return x > -708.0 ? res : ((x != x) ? x : 0.0);
+}
 
 }  // namespace

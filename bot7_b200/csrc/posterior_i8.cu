@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(128)
 cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const double* __restrict__ Xt, int N, int Np,
                   const double* __restrict__ par, double inv_tau, const double* __restrict__ alpha, int8_t* __restrict__ ksS,
                   double* __restrict__ meanP) {
-  __shared__ double s_x[DT][64];
+  __shared__ __align__(16) double s_x[DT][64];
   __shared__ double s_w[DT];
   __shared__ double s_tab[64];
-  __shared__ double s_al[64];
+  __shared__ __align__(16) double s_al[64];
   __shared__ double s_dot[64];
   if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
   const int ct = blockIdx.x, kb64 = blockIdx.y, KS_ALL = Np / KB;
@@ -141,32 +141,47 @@ cov_slices_kernel(const double* __restrict__ A, long long rows, int d, const dou
   // sf2 / tau * 2^54: tau is a power of two, so scaling sf2 first rounds exactly like scaling the product afterwards
   const double sf2s = par[B7_MAX_DIMS] * inv_tau * 18014398509481984.0;
   double dot = 0.0;
+  double w[DT];
+#pragma unroll
+  for (int j = 0; j < DT; ++j) w[j] = s_w[j];
+  ExpNegK K;
+  K.init();
+  const bool live = row < rows;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
   const int kc = (threadIdx.x >> 6) + 2 * half;
   uint32_t pk[4][NS];
   unsigned long long z[4];
+  // two observations per step (one LDS.128 per dimension); the bounds are selects, not branches (k is warp-uniform, the
+  // padded columns of s_x are zeros, a dead row computes on zeros): the kernel is bound by its instruction count
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 16; i += 2) {
     const int kk = kc * 16 + i, k = kb64 * 64 + kk;
-    double val = 0.0;
-    if (row < rows && k < N) {
-      double r2 = 0.0;
+    double r2a = 0.0, r2b = 0.0;
 #pragma unroll
-      for (int j = 0; j < DT; ++j) {
-        const double t = (a[j] - s_x[j][kk]) * s_w[j];
-        r2 = fma(t, t, r2);
-      }
-      if (KERNEL == B7_KERNEL_ARDSE) {
-        val = sf2s * exp_neg(-0.5 * r2, s_tab);
-      } else {
-        const double rr = sqrt(r2), s5r = 2.23606797749978969641 * rr;
-        val = sf2s * ((1.0 + s5r + (5.0 / 3.0) * r2) * exp_neg(-s5r, s_tab));
-      }
+    for (int j = 0; j < DT; ++j) {
+      const double2 x2 = *reinterpret_cast<const double2*>(&s_x[j][kk]);
+      const double ta = (a[j] - x2.x) * w[j], tb = (a[j] - x2.y) * w[j];
+      r2a = fma(ta, ta, r2a);
+      r2b = fma(tb, tb, r2b);
     }
-    dot = fma(val, s_al[kk], dot);
-    z[i & 3] = digit_bytes_scaled(val);
-    if ((i & 3) == 3) pack4(z, pk[i >> 2]);
+    double va, vb;
+    if (KERNEL == B7_KERNEL_ARDSE) {
+      va = sf2s * exp_neg_k(-0.5 * r2a, s_tab, K);
+      vb = sf2s * exp_neg_k(-0.5 * r2b, s_tab, K);
+    } else {
+      const double ra = sqrt(r2a), s5a = 2.23606797749978969641 * ra, rb = sqrt(r2b), s5b = 2.23606797749978969641 * rb;
+      va = sf2s * ((1.0 + s5a + (5.0 / 3.0) * r2a) * exp_neg_k(-s5a, s_tab, K));
+      vb = sf2s * ((1.0 + s5b + (5.0 / 3.0) * r2b) * exp_neg_k(-s5b, s_tab, K));
+    }
+    va = (live && k < N) ? va : 0.0;
+    vb = (live && k + 1 < N) ? vb : 0.0;
+    const double2 al = *reinterpret_cast<const double2*>(&s_al[kk]);
+    dot = fma(va, al.x, dot);
+    dot = fma(vb, al.y, dot);
+    z[i & 3] = digit_bytes_scaled(va);
+    z[(i & 3) + 1] = digit_bytes_scaled(vb);
+    if ((i & 3) == 2) pack4(z, pk[i >> 2]);
   }
   const int gkc = kb64 * 4 + kc, ks = gkc / KC, kcc = gkc % KC;
   int8_t* dst = PAIR ? ksS + (((long long)ct * KS_ALL + ks) * 2 + (c >> 5)) * B_HALF + kcc * (TNH * 16) + (c & 31) * 16
