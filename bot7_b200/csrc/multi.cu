@@ -350,6 +350,23 @@ int b7_gp_fit_sharded(b7_comm* c, int kernel, const double* X, const double* y, 
     return b7_gp_prepare_gather(out[i], (int)s0, (int)cnt);
   });
   auto fail = [&](int code) { for (int i = 0; i < n; ++i) { b7_gp_free(out[i]); out[i] = nullptr; } return code; };
+  // one process per GPU: agree on the outcome of phase 1 before anybody enters the big exchange (a rank that failed,
+  // e.g. out of memory, must not leave the others waiting inside ncclAllGather)
+  if (c->world > n) {
+    b7_ctx* x = c->ctx[0];
+    cudaSetDevice(x->device);
+    double mine = rc < 0 ? 1.0 : 0.0;
+    std::string my_msg = rc < 0 ? b7_last_error() : "";
+    std::vector<double> all((size_t)c->world, 0.0);
+    cudaError_t e = cudaMemcpyAsync(c->triple[0] + c->rank0, &mine, sizeof(double), cudaMemcpyHostToDevice, x->stream);
+    ncclResult_t r = e == cudaSuccess ? g_nccl.AllGather(c->triple[0] + c->rank0, c->triple[0], 1, ncclFloat64, c->nccl[0], x->stream) : 1;
+    if (r == 0) e = cudaMemcpyAsync(all.data(), c->triple[0], all.size() * sizeof(double), cudaMemcpyDeviceToHost, x->stream);
+    if (r == 0 && e == cudaSuccess) e = cudaStreamSynchronize(x->stream);
+    if (r != 0 || e != cudaSuccess) { b7_set_error("gp_fit_sharded: status exchange failed"); return fail(B7_ERR_NCCL); }
+    for (int q = 0; q < c->world; ++q)
+      if (all[q] != 0.0 && rc == 0) { b7_set_error("gp_fit_sharded: rank %d failed in its share of the fit", q); rc = B7_ERR_STATE; }
+    if (rc < 0 && !my_msg.empty()) b7_set_error("%s", my_msg.c_str());
+  }
   if (rc < 0) return fail(rc);
   // 2. one exchange, in the form the posterior pass reads
   const bool i8 = out[0]->ctx->use_i8 && out[0]->Np <= B7_I8_MAX_NP;
