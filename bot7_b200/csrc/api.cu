@@ -99,7 +99,14 @@ int grow(b7_ctx* ctx, double** p, size_t* have, size_t need_bytes) {
 inline int64_t pad128(int64_t n) { return (n + 127) / 128 * 128; }
 
 // candidates per posterior launch: one 128-candidate tile per SM = one full wave
-inline int64_t panel_rows(b7_ctx* ctx) { return (int64_t)ctx->sm_count * 128; }
+// Smaller fits get proportionally larger panels (up to 8x), so that a launch stays long against its fixed costs (barrier and
+// TMEM set-up, pipeline fill and drain: a 148 x 128 panel at N = 512 was a 97 us launch at 0.35 of the INT8 peak) while
+// the K* panel buffer keeps its size (rows x Np).
+inline int64_t panel_rows(b7_ctx* ctx, int Np = 4096) {
+  const int64_t base = (int64_t)ctx->sm_count * 128;
+  const int64_t f = Np >= 4096 ? 1 : std::min<int64_t>(8, 4096 / std::max(Np, 128));
+  return base * f;
+}
 
 int sync_removed(b7_grid* g) {
   if (!g->removed_dirty) return 0;
@@ -865,7 +872,7 @@ int b7_gp_predict(b7_gp* gp, int s, const double* Xs, int64_t M, double* mean, d
   B7_CHECK(require_predict_state(gp));
   b7_ctx* ctx = gp->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
-  const int64_t P = panel_rows(ctx);
+  const int64_t P = panel_rows(ctx, gp->Np);
   B7_CHECK(grow(ctx, &ctx->xs_stage, &ctx->xs_bytes, (size_t)std::min(P, pad128(M)) * gp->d * 8));
   B7_CHECK(grow(ctx, &ctx->moments, &ctx->moments_bytes, (size_t)2 * std::min(P, pad128(M)) * 8));
   for (int64_t c0 = 0; c0 < M; c0 += P) {
@@ -921,7 +928,7 @@ int b7_acq_score_range(b7_gp* gp, b7_grid* grid, int64_t row0, int64_t count, in
   b7_ctx* ctx = gp->ctx;
   B7_CUDA(cudaSetDevice(ctx->device));
   B7_CHECK(sync_removed(grid));
-  const int64_t P = panel_rows(ctx), Pp = std::min(P, pad128(std::max<int64_t>(count, 1)));
+  const int64_t P = panel_rows(ctx, gp->Np), Pp = std::min(P, pad128(std::max<int64_t>(count, 1)));
   const int S = gp->S;
   B7_CHECK(grow(ctx, &ctx->moments, &ctx->moments_bytes, (size_t)2 * S * Pp * 8));
   const int64_t n_panels = (count + P - 1) / P;
