@@ -50,8 +50,8 @@ int  b7_last_stage_ms(b7_ctx* ctx, int stage, double* ms_total, int64_t* launche
 /* Which tensor pipe carries the posterior pass (V = L^-1 K*^T, N^2 flop per candidate per draw):
  *   B7_PATH_FP64_DMMA  fp64 operands on DMMA tiles (posterior.cu);
  *   B7_PATH_INT8_OZAKI both operands split error-free into 7 radix-256 int8 slices, 28 exact int32 products on
- *                      tcgen05.mma.kind::i8, recombined in fp64 (posterior_i8.cu): same results to ~5e-14 sf2,
- *                      2.6x the throughput.  With this path the k = 512 trailing updates of batched factorisations
+ *                      tcgen05.mma.kind::i8 (CTA pairs), recombined in fp64 (posterior_i8.cu): variance to ~1e-12 sf2,
+ *                      the mean an fp64 dot product k*^T alpha; 3x the throughput.  With this path the k = 512 trailing updates of batched factorisations
  *                      (potrf_i8.cu) and the inversion of the factors (trtri_i8.cu) use the same slicing
  *                      (B7_POTRF_I8=0 / B7_TRTRI_I8=0 keep those in FP64).  Default; B7_POSTERIOR_I8=0 in the
  *                      environment selects DMMA; fits with more than 16384 observations always use DMMA (int32
