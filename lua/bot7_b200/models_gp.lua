@@ -93,23 +93,26 @@ end
 ---------------- log p(y | h) + log p(h): the density the slice sampler evaluates (samplers/slice.lua:100-103).
 -- X and y stay resident between evaluations (b7_gp_refit on one handle of `spec_width` slots); a failed
 -- factorisation or a non-finite likelihood is -inf, so the sampler rejects the point.
-function model:log_density_batch(H, X, Y)
+function model:log_density_batch(H, X, Y, W)
   local H = self:parse_hypers(H):contiguous():double()
-  local k, W = H:size(1), math.max(self.config.spec_width, 1)
+  local k = H:size(1)
+  local W = W or math.max(self.config.spec_width, 1)           -- slots of the resident handle (one handle per width)
   local sd   = self.config.prior_std
   local out  = torch.DoubleTensor(k)
   local pad  = torch.DoubleTensor(W, H:size(2))
   local info, logml, jit = ffi.new('int[?]', W), torch.DoubleTensor(W), torch.DoubleTensor(W)
+  self._density = self._density or {}
   for c0 = 1, k, W do
     local n = math.min(W, k - c0 + 1)
     pad:narrow(1, 1, n):copy(H:narrow(1, c0, n))
     for r = n + 1, W do pad[r]:copy(H[c0 + n - 1]) end       -- short batches repeat their last row
-    if self._density == nil or self._density_X ~= X or self._density_Y ~= Y then
+    local slot = self._density[W]
+    if slot == nil or slot.X ~= X or slot.Y ~= Y then
       local gp, lm, inf = self:fit(X, Y, pad, B.C.B7_FIT_LOGML_ONLY)
-      self._density, self._density_X, self._density_Y = gp, X, Y
+      self._density[W] = {gp = gp, X = X, Y = Y}
       logml:copy(lm); ffi.copy(info, inf, W * ffi.sizeof('int'))
     else
-      B.check(B.C.b7_gp_refit(self._density, pad:data(), B.C.B7_FIT_LOGML_ONLY, info, logml:data(), jit:data()), 'b7_gp_refit')
+      B.check(B.C.b7_gp_refit(slot.gp, pad:data(), B.C.B7_FIT_LOGML_ONLY, info, logml:data(), jit:data()), 'b7_gp_refit')
     end
     for i = 1, n do
       local lp = logml[i]
@@ -120,8 +123,9 @@ function model:log_density_batch(H, X, Y)
   return out
 end
 
+-- one evaluation at a time (what bot7.samplers.slice asks for): a handle with a single slot, 4.3 ms at N = 4096
 function model:log_density(h, X, Y)
-  return self:log_density_batch(self:parse_hypers(h), X, Y)[1]
+  return self:log_density_batch(self:parse_hypers(h), X, Y, 1)[1]
 end
 
 ---------------- bots/bayesopt.lua:68,74: slice-sample the hyper-parameter posterior, keep the chain state.
