@@ -651,8 +651,11 @@ int b7_i8_cov_slices(b7_ctx* ctx, cudaStream_t st, int kernel, const double* A, 
   if (d <= 4) B7_COV_SLICES(4);
   if (d <= 6) B7_COV_SLICES(6);
   if (d <= 8) B7_COV_SLICES(8);
+  if (d <= 12) B7_COV_SLICES(12);
   if (d <= 16) B7_COV_SLICES(16);
+  if (d <= 20) B7_COV_SLICES(20);
   if (d <= 24) B7_COV_SLICES(24);
+  if (d <= 32) B7_COV_SLICES(32);
   B7_COV_SLICES(40);
 #undef B7_COV_SLICES
 }
