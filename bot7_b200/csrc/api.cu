@@ -675,6 +675,8 @@ int b7_gp_fit(b7_ctx* ctx, int kernel, const double* X, const double* y, int N, 
       (rc = dev_alloc(ctx, &gp->tt, (size_t)S * B7_NB * Np)) ||
       (rc = dev_alloc(ctx, &gp->logdet, (size_t)S)) || (rc = dev_alloc(ctx, &gp->info, (size_t)S)))
     return fail(rc);
+  // diag_kernel only writes the lower triangles of the inverted diagonal blocks: the zeros above them are set here, once
+  if (cudaMemsetAsync(gp->dinv, 0, (size_t)S * ds * sizeof(double), ctx->stream) != cudaSuccess) return fail(B7_ERR_CUDA);
   gp->y_host.assign(y, y + N);
   set_hypers_host(gp, hyp);
   std::vector<double> xt((size_t)d * Np, 0.0), r;

@@ -21,7 +21,11 @@
 //           long-k launches with a quarter of the read-modify-write traffic on C.
 // Inversion (LAPACK dtrtri order, in place, column sweep from the right):
 //   T = L[j+1:, j] * inv(L_jj)  (stored transposed), then  X[j+1:, j] = -Linv[j+1:, j+1:] * T.
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 #include "b7_internal.h"
 #include "gemm_tile.cuh"
@@ -37,8 +41,8 @@ constexpr int DLD = 132;            // 132 = 4 mod 16: DMMA fragment loads (row-
 constexpr int SB = 16;              // sub-block width inside the 128 block
 constexpr int DSLD = 20;            // leading dimension of the 16x16 sub-block inverses
 constexpr int TLD = 68;             // scratch of the recursive inversion (64 x 68)
-// shared: M[128][132] | DS[8][16][20] | T[64][68] | LD[16][17] | pivs,invs,rj,lg [4][128]
-constexpr int DIAG_SMEM = (NBK * DLD + 8 * SB * DSLD + 64 * TLD + SB * 17 + 4 * NBK) * 8;
+// shared: M[128][132] | DS[8][16][20] | T[64][68] | pivs,invs,rj,lg [4][128]
+constexpr int DIAG_SMEM = (NBK * DLD + 8 * SB * DSLD + 64 * TLD + 4 * NBK) * 8;
 
 // one 8x8 accumulator fragment: c += sign * A[m.., k0..k1) * op(B);  A row-major (k contiguous).
 // NN = false: B is [n][k] row-major (C = A B^T);  NN = true: B is [k][n] row-major (C = A B).
@@ -46,200 +50,345 @@ template <bool NN>
 __device__ __forceinline__ void frag_mac(double& c0, double& c1, const double* __restrict__ A, int lda,
                                          const double* __restrict__ B, int ldb, int k_begin, int k_end, double sign, int lane) {
   const int r = lane >> 2, c = lane & 3;
-  for (int k = k_begin; k < k_end; k += 4) {
+#pragma unroll 2
+  for (int k = k_begin; k < k_end; k += 4) {     // every caller's k range is a multiple of 8
     const double a = sign * A[r * lda + k + c];
     const double b = NN ? B[(k + c) * ldb + r] : B[r * ldb + k + c];
     dmma884(c0, c1, a, b);
   }
 }
 
-// 1/sqrt(x) without the library's out-of-line slow path (its CALL forces the 16 row registers of the
-// factorisation below through local memory): float seed + three Newton steps, <= 2 ulp for normal x.
-// A normal positive x is first scaled by an even power of two into [1, 4) (exact, on the exponent bits), so that a
-// pivot above FLT_MAX or below FLT_MIN no longer loses the float seed (inf -> seed 0 -> result 0; denormal -> NaN);
-// x <= 0, NaN, inf or denormal keeps the plain path and gives inf / NaN / 0, which the info logic flags.
-__device__ __forceinline__ double rsqrt_nr(double x) {
-  const long long bits = __double_as_longlong(x);
-  const int ef = (int)((bits >> 52) & 0x7ff);
-  double m = x, scale = 1.0;
-  if (bits > 0 && ef >= 1 && ef <= 2046) {
-    const int e2 = (ef - 1023) & ~1;                                        // even, rounds towards -inf
-    m = __longlong_as_double(bits - ((long long)e2 << 52));                 // x 2^-e2 in [1, 4)
-    scale = __longlong_as_double((long long)(1023 - e2 / 2) << 52);         // 2^(-e2 / 2)
-  }
-  double y = (double)rsqrtf((float)m);
-  const double hx = 0.5 * m;
-#pragma unroll
-  for (int it = 0; it < 3; ++it) y = y * fma(-hx * y, y, 1.5);
-  return y * scale;
-}
+// tools/diag_probe.cu compiles this file with B7_DIAG_STAMPS to get a cycle stamp per phase of the diagonal-block kernel
+#ifdef B7_DIAG_STAMPS
+__device__ long long b7_diag_stamps[128];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) b7_diag_stamps[i] = clock64(); } while (0)
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
 
 // ---- diagonal block: potf2 + inverse + x_j + logdet + info -------------------------------------
-// Blocked inside shared memory so that almost all arithmetic is DMMA on 8x8 fragments:
-//   for each 16-wide sub-block: warp 0 factors the 16x16 diagonal piece in registers (shuffles) and
-//   inverts it; all warps then form the sub-panel L21 = A21 inv(L11)^T and the trailing update
-//   A22 -= L21 L21^T as fragment products.  The 128x128 inverse is assembled afterwards by
-//   recursive doubling ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]]) for h = 16, 32, 64,
-//   again as fragment products, in place.
+// One CTA per draw; the block lives in shared memory (M, row-major, leading dimension 132).  The block column count
+// times the duration of this kernel is the floor of a single-factor fit, so it is organised around its dependent chain:
+//   * 16-wide sub-blocks.  Warp 0 ("chain") factors the 16x16 diagonal piece in registers: lane = row, the column is
+//     broadcast by shuffles, every lane keeps its own copy of the running diagonal (no pivot broadcast), and the
+//     reciprocal square root is a MUFU.RSQ64H seed + one cubic step with the scaling of the column folded in
+//     (5 dependent FP64 operations per column; tools/lat_probe.cu: DFMA 8.3, SHFL 26, seed 19 cycles).
+//   * lanes 16..31 of the chain warp carry the identity below the piece: the same eliminations turn [A; I] into
+//     [L; L^-T], so the inverse of the piece costs no instruction of its own.
+//   * look-ahead: the chain warp itself forms the 16 rows of the sub-panel and the 3 fragments of the trailing update
+//     that the next piece needs and goes on factoring; warps 1..15 do the rest of the sub-panel
+//     (L21 = A21 inv(L11)^T) and of the trailing update (A22 -= L21 L21^T) as DMMA fragment products behind it and
+//     write the finished 16 columns of L to global memory.  Named barriers: S1 = "piece inverse and the chain's rows
+//     are ready" (chain arrives, the others wait), U = between sub-panel and trailing update (warps 1..15),
+//     S2 = "trailing update done" (the others arrive, the chain waits before it touches the next rows).
+//   * the 128x128 inverse is assembled by recursive doubling ([[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]])
+//     for h = 16, 32, 64 as fragment products, in place, fragments dealt so that every warp gets the same k length.
+// History (tools/diag_probe.cu, cycles): 152 k with a lane-0 branch per column, float seed + 3 Newton steps, a separate
+// inverse of the piece and no look-ahead (factor 79 k, inverse 18 k, updates 17 k, doubling 18 k, I/O 16 k).
+constexpr int BAR_S1 = 1, BAR_U = 2, BAR_S2 = 3;
+constexpr int UPD_THREADS = (DIAG_WARPS - DIAG_WARPS / 4) * 32;   // warps with (warp & 3) != 0
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ double rsq_seed(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+// sub-panel of row group g (8 rows from i0 + 8 g): L21 = A21 * inv(L11)^T, all 16 columns, in place
+__device__ __forceinline__ void diag_subpanel(double* M, const double* DSp, int i0, int j0, int g, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  double* Arow = M + (i0 + 8 * g) * DLD + j0;
+  double a4[4];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) a4[k4] = Arow[r * DLD + 4 * k4 + c];
+  double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    dmma884(c00, c01, a4[k4], DSp[r * DSLD + 4 * k4 + c]);
+    dmma884(c10, c11, a4[k4], DSp[(8 + r) * DSLD + 4 * k4 + c]);
+  }
+  __syncwarp();
+  *reinterpret_cast<double2*>(Arow + r * DLD + 2 * c) = make_double2(c00, c01);
+  *reinterpret_cast<double2*>(Arow + r * DLD + 8 + 2 * c) = make_double2(c10, c11);
+}
+
+// the chain warp's look-ahead: row groups 0 and 1 of the sub-panel with their four accumulator chains interleaved ...
+__device__ __forceinline__ void diag_subpanel_pair(double* M, const double* DSp, int i0, int j0, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  double* Arow = M + i0 * DLD + j0;
+  double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    a0[k4] = Arow[r * DLD + 4 * k4 + c];
+    a1[k4] = Arow[(8 + r) * DLD + 4 * k4 + c];
+    b0[k4] = DSp[r * DSLD + 4 * k4 + c];
+    b1[k4] = DSp[(8 + r) * DSLD + 4 * k4 + c];
+  }
+  double c00 = 0, c01 = 0, c10 = 0, c11 = 0, e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    dmma884(c00, c01, a0[k4], b0[k4]);
+    dmma884(c10, c11, a0[k4], b1[k4]);
+    dmma884(e00, e01, a1[k4], b0[k4]);
+    dmma884(e10, e11, a1[k4], b1[k4]);
+  }
+  __syncwarp();
+  *reinterpret_cast<double2*>(Arow + r * DLD + 2 * c) = make_double2(c00, c01);
+  *reinterpret_cast<double2*>(Arow + r * DLD + 8 + 2 * c) = make_double2(c10, c11);
+  *reinterpret_cast<double2*>(Arow + (8 + r) * DLD + 2 * c) = make_double2(e00, e01);
+  *reinterpret_cast<double2*>(Arow + (8 + r) * DLD + 8 + 2 * c) = make_double2(e10, e11);
+}
+
+// ... and the three fragments (0,0), (1,0), (1,1) of the trailing update, i.e. the next 16x16 piece
+__device__ __forceinline__ void diag_trail_next_piece(double* M, int i0, int j0, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  const double* L0 = M + i0 * DLD + j0;
+  double a0[4], a1[4];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    a0[k4] = L0[r * DLD + 4 * k4 + c];
+    a1[k4] = L0[(8 + r) * DLD + 4 * k4 + c];
+  }
+  double2* p00 = reinterpret_cast<double2*>(M + (i0 + r) * DLD + i0 + 2 * c);
+  double2* p10 = reinterpret_cast<double2*>(M + (i0 + 8 + r) * DLD + i0 + 2 * c);
+  double2* p11 = reinterpret_cast<double2*>(M + (i0 + 8 + r) * DLD + i0 + 8 + 2 * c);
+  double2 v00 = *p00, v10 = *p10, v11 = *p11;
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    dmma884(v00.x, v00.y, -a0[k4], a0[k4]);
+    dmma884(v10.x, v10.y, -a1[k4], a0[k4]);
+    dmma884(v11.x, v11.y, -a1[k4], a1[k4]);
+  }
+  *p00 = v00; *p10 = v10; *p11 = v11;
+}
+
+// trailing fragment (gi, gk): C -= L21[gi] L21[gk]^T over the 16 columns from j0
+__device__ __forceinline__ void diag_trail_frag(double* M, int i0, int j0, int gi, int gk, int lane) {
+  const int r = lane >> 2, c = lane & 3;
+  double2* cp = reinterpret_cast<double2*>(M + (i0 + 8 * gi + r) * DLD + i0 + 8 * gk + 2 * c);
+  double2 cv = *cp;
+  frag_mac<false>(cv.x, cv.y, M + (i0 + 8 * gi) * DLD + j0, DLD, M + (i0 + 8 * gk) * DLD + j0, DLD, 0, SB, -1.0, lane);
+  *cp = cv;
+}
+
+// one k-tile (16 columns from 16 kt, all 128 rows) of the block back to global memory in tiled order, upper part zero;
+// a thread moves 16 bytes, consecutive threads consecutive addresses
+__device__ __forceinline__ void diag_store_tile(double* __restrict__ blk, const double* M, int kt, int t, int nthreads) {
+  for (int u = t; u < NBK * 8; u += nthreads) {          // u = (g4 * 128 + row) * 2 + half
+    const int i = (u >> 1) & 127, k0 = kt * TILE_K + (u >> 8) * 4 + (u & 1) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(M + i * DLD + k0);
+    *reinterpret_cast<double2*>(blk + kt * TILE_DOUBLES + u * 2) = make_double2(k0 <= i ? v.x : 0.0, k0 + 1 <= i ? v.y : 0.0);
+  }
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
-diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, double* __restrict__ dinv,
-            double* __restrict__ dinvT, long long dinv_stride, double* __restrict__ beta, double* __restrict__ logdet,
-            int* __restrict__ info, int s0) {
+diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, double* __restrict__ dinv, long long dinv_stride,
+            double* __restrict__ beta, double* __restrict__ logdet, int* __restrict__ info, int s0) {
   extern __shared__ __align__(16) double sm[];
   double* M = sm;
   double* DS = M + NBK * DLD;
   double* T = DS + 8 * SB * DSLD;
-  double* LD = T + 64 * TLD;
-  double* pivs = LD + SB * 17;
+  double* pivs = T + 64 * TLD;
   double* invs = pivs + NBK;
   double* rj = invs + NBK;
   double* lg = rj + NBK;
+  __shared__ int s_info;
   const int s = s0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, c = lane & 3;
+  DIAG_STAMP(0);
   double* blk = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, j, j * (NBK / TILE_K));   // 8 tiles of block (j, j)
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    // e enumerates the tiled order [kt][g4][row][kk]
-    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
-    M[i * DLD + k] = (k <= i) ? blk[e] : 0.0;
+#pragma unroll 8
+  for (int u = tid; u < NBK * NBK / 2; u += DIAG_THREADS) {
+    // u enumerates pairs of doubles in the tiled order [kt][g4][row][kk]: 16 bytes per thread, consecutive threads
+    // consecutive addresses; pairs above the diagonal are not read
+    const int i = (u >> 1) & 127, k0 = (u >> 10) * TILE_K + ((u >> 8) & 3) * 4 + (u & 1) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (k0 <= i) v = *reinterpret_cast<const double2*>(blk + 2 * u);
+    *reinterpret_cast<double2*>(M + i * DLD + k0) = make_double2(v.x, k0 + 1 <= i ? v.y : 0.0);
   }
   if (tid < NBK) rj[tid] = beta[(long long)s * Np + j * NBK + tid];
-  int my_info = 0;
+  if (tid == 0) s_info = 0;
   __syncthreads();
+  DIAG_STAMP(1);
 
-  for (int p = 0; p < NBK / SB; ++p) {
-    const int j0 = p * SB, i0 = j0 + SB, G = (NBK - i0) / 8;
-    // (a) 16x16 diagonal piece: factor (lane = row, column broadcast by shuffle), then invert by columns
-    if (warp == 0) {
-      double a[SB];
+  if (warp == 0) {
+    // ---- chain warp ----
+    const bool is_row = lane < SB;
+    const int li = lane & (SB - 1);
+    int my_info = 0;
+    for (int p = 0; p < NBK / SB; ++p) {
+      const int j0 = p * SB, i0 = j0 + SB;
+      double a[SB], d[SB];
 #pragma unroll
-      for (int k = 0; k < SB; ++k) a[k] = (lane < SB && k <= lane) ? M[(j0 + lane) * DLD + j0 + k] : 0.0;
+      for (int k = 0; k < SB; ++k) {
+        a[k] = is_row ? M[(j0 + li) * DLD + j0 + k] : (k == li ? 1.0 : 0.0);
+        d[k] = M[(j0 + k) * DLD + j0 + k];
+      }
+      double mypiv = 1.0, myinv = 1.0;
 #pragma unroll
       for (int q = 0; q < SB; ++q) {
-        const double piv = __shfl_sync(0xffffffffu, a[q], q);
-        const double inv = rsqrt_nr(piv);
-        if (lane == 0) {
-          pivs[j0 + q] = piv;
-          invs[j0 + q] = inv;
-          // LAPACK info: first pivot that is not positive -- or whose reciprocal root is not a finite positive number
-          if ((!(piv > 0.0) || !(inv > 0.0) || inv > 1.79e308) && my_info == 0) my_info = j * NBK + j0 + q + 1;
-        }
-        const double my = a[q] * inv;   // L[lane][q] for lane > q
+        // inv = piv^-1/2: y (1 + e/2 + 3 e^2/8) with e = 1 - piv y^2 (|e| < 2^-19 from the seed: truncation below 2^-58);
+        // my = a_q inv with the product by a_q folded into the correction
+        const double piv = d[q];
+        const double y = rsq_seed(piv);
+        const double ay = a[q] * y, t = y * y;
+        const double e = fma(-piv, t, 1.0);
+        const double u = fma(e, 0.375, 0.5);
+        const double my = fma(u, ay * e, ay);
+        const double inv = fma(u, y * e, y);
+        if (lane == q) { mypiv = piv; myinv = inv; }
 #pragma unroll
-        for (int k = 1; k < SB; ++k) {      // constant trip count: keeps a[] in registers
+        for (int k = 0; k < SB; ++k) {      // constant trip count: keeps a[], d[] in registers
           if (k > q) {
+            // entries above the diagonal (lane < k <= 15) pick up values that are never read
             const double lk = __shfl_sync(0xffffffffu, my, k);
-            if (lane >= k) a[k] = fma(-my, lk, a[k]);
+            a[k] = fma(-my, lk, a[k]);
+            d[k] = fma(-lk, lk, d[k]);
           }
         }
-        a[q] = (lane > q) ? my : (lane == q ? piv * inv : a[q]);
+        a[q] = my;
       }
-      if (lane < SB) {
+      // LAPACK info: first pivot that is not positive -- or whose reciprocal root is not a finite positive number
+      const unsigned bad = __ballot_sync(0xffffffffu, is_row && (!(mypiv > 0.0) || !(myinv > 0.0) || myinv > 1.79e308));
+      if (bad != 0u && my_info == 0) my_info = j * NBK + j0 + __ffs((int)bad);
+      if (is_row) {
 #pragma unroll
-        for (int k = 0; k < SB; ++k) {
-          const double v = (k <= lane) ? a[k] : 0.0;
-          M[(j0 + lane) * DLD + j0 + k] = v;
-          LD[lane * 17 + k] = v;
+        for (int k = 0; k < SB; k += 2)
+          *reinterpret_cast<double2*>(M + (j0 + lane) * DLD + j0 + k) = make_double2(k <= lane ? a[k] : 0.0, k + 1 <= lane ? a[k + 1] : 0.0);
+        pivs[j0 + lane] = mypiv;
+        invs[j0 + lane] = myinv;
+      } else {
+        // lane 16 + col holds column col of the inverse: a[row] = X[row][col] (zero above the diagonal)
+#pragma unroll
+        for (int i = 0; i < SB; ++i) DS[(p * SB + i) * DSLD + li] = a[i];
+      }
+      __syncwarp();
+      DIAG_STAMP(2 + 3 * p);
+      if (p < NBK / SB - 1) {
+        if (p >= 1) nbar_sync(BAR_S2, 32 + UPD_THREADS);      // trailing update p - 1 is complete
+        DIAG_STAMP(3 + 3 * p);
+        diag_subpanel_pair(M, DS + p * SB * DSLD, i0, j0, lane);
+        if (p < NBK / SB - 2) {
+          fence_cta();
+          nbar_arrive(BAR_S1, 32 + UPD_THREADS);
         }
-      }
-      __syncwarp();
-      // column `lane` of the inverse: x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii   (x_k = 0 for k < c)
-      double x[SB];
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        double acc = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < SB; ++k)
-          if (k < i) acc = fma(-LD[i * 17 + k], x[k], acc);
-        x[i] = (i >= lane) ? acc * invs[j0 + i] : 0.0;
-      }
-      if (lane < SB) {
-#pragma unroll
-        for (int i = 0; i < SB; ++i) DS[(p * SB + i) * DSLD + lane] = x[i];
+        __syncwarp();
+        diag_trail_next_piece(M, i0, j0, lane);
+        __syncwarp();
+        DIAG_STAMP(4 + 3 * p);
       }
     }
-    __syncthreads();
-    // (b) sub-panel: rows below, L21 = A21 * inv(L11)^T; one warp owns all 16 columns of its 8 rows
-    for (int g = warp; g < G; g += DIAG_WARPS) {
-      double* Arow = M + (i0 + 8 * g) * DLD + j0;
-      double a4[4];
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) a4[k4] = Arow[r * DLD + 4 * k4 + c];
-      double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        dmma884(c00, c01, a4[k4], DS[(p * SB + r) * DSLD + 4 * k4 + c]);
-        dmma884(c10, c11, a4[k4], DS[(p * SB + 8 + r) * DSLD + 4 * k4 + c]);
+    if (lane == 0) s_info = my_info;
+  } else if ((warp & 3) != 0) {
+    // ---- update warps: sub-blocks 0..5 (the chain's look-ahead covers all of sub-block 6).  Warps 4, 8 and 12 sit out:
+    //      they would share the chain warp's scheduler and FP64 pipe (a DFMA of the chain queued behind their DMMAs:
+    //      5.5 k instead of 2.9 k cycles per piece) ----
+    const int uw = warp - 1 - (warp >> 2), ut = uw * 32 + lane;
+    constexpr int UW = UPD_THREADS / 32;
+    for (int p = 0; p < NBK / SB - 2; ++p) {
+      const int j0 = p * SB, i0 = j0 + SB, G = (NBK - i0) / 8;
+      nbar_sync(BAR_S1, 32 + UPD_THREADS);
+      if (ut < SB) lg[j0 + ut] = log(pivs[j0 + ut] * invs[j0 + ut]);
+      for (int g = 2 + uw; g < G; g += UW) diag_subpanel(M, DS + p * SB * DSLD, i0, j0, g, lane);
+      nbar_sync(BAR_U, UPD_THREADS);
+      const int n_frag = G * (G + 1) / 2;
+      int gi = 2, rem = uw;                 // fragment 3 + uw in the order (gi, gk <= gi); fragments 0..2 are the chain's
+      for (int f = 3 + uw; f < n_frag; f += UW) {
+        while (rem > gi) { rem -= gi + 1; ++gi; }
+        diag_trail_frag(M, i0, j0, gi, rem, lane);
+        rem += UW;
       }
-      __syncwarp();
-      *reinterpret_cast<double2*>(Arow + r * DLD + 2 * c) = make_double2(c00, c01);
-      *reinterpret_cast<double2*>(Arow + r * DLD + 8 + 2 * c) = make_double2(c10, c11);
+      fence_cta();
+      nbar_arrive(BAR_S2, 32 + UPD_THREADS);
+      diag_store_tile(blk, M, p, ut, UPD_THREADS);          // columns j0 .. j0 + 15 are final
     }
-    __syncthreads();
-    // (c) trailing update on the lower fragments: A22 -= L21 L21^T
-    const int n_frag = G * (G + 1) / 2;
-    for (int f = warp; f < n_frag; f += DIAG_WARPS) {
-      int gi = 0, rem = f;
-      while (rem > gi) { rem -= gi + 1; ++gi; }
-      const int gk = rem;
-      double2* cp = reinterpret_cast<double2*>(M + (i0 + 8 * gi + r) * DLD + i0 + 8 * gk + 2 * c);
-      double2 cv = *cp;
-      frag_mac<false>(cv.x, cv.y, M + (i0 + 8 * gi) * DLD + j0, DLD, M + (i0 + 8 * gk) * DLD + j0, DLD, 0, SB, -1.0, lane);
-      *cp = cv;
-    }
-    __syncthreads();
-  }
-  // L block back to global (upper part zero)
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
-    blk[e] = (k <= i) ? M[i * DLD + k] : 0.0;
-  }
-  if (tid < NBK) lg[tid] = log(pivs[tid] * invs[tid]);
-  __syncthreads();
-  // ---- inverse, in place: diagonal 16x16 pieces first, then recursive doubling ----
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {
-    const int i = e >> 7, k = e & 127;
-    if ((i >> 4) == (k >> 4)) M[i * DLD + k] = DS[i * DSLD + (k & 15)];       // includes the zero upper part
-    else if (k > i) M[i * DLD + k] = 0.0;
   }
   __syncthreads();
+  DIAG_STAMP(26);
+  diag_store_tile(blk, M, NBK / SB - 2, tid, DIAG_THREADS);
+  diag_store_tile(blk, M, NBK / SB - 1, tid, DIAG_THREADS);
+  if (tid >= NBK - 2 * SB && tid < NBK) lg[tid] = log(pivs[tid] * invs[tid]);
+  __syncthreads();
+  // ---- inverse, in place: the 16x16 pieces first, then recursive doubling ----
+  for (int e = tid; e < NBK * SB; e += DIAG_THREADS) {
+    const int i = e >> 4, k = e & 15;
+    M[i * DLD + (i & ~15) + k] = DS[i * DSLD + k];       // includes the zero upper part of the piece
+  }
+  __syncthreads();
+  DIAG_STAMP(27);
   for (int h = SB; h < NBK; h <<= 1) {
-    const int fpr = h / 8, n_pairs = NBK / (2 * h), per_pair = fpr * fpr;
+    // fragment costs are (k length) h/8 - fn in the first phase and fi + 1 in the second: a warp takes that index from
+    // both ends of the range so that every warp has the same total (h / 16 fragments per warp and phase)
+    const int fpr = h / 8, wpp = DIAG_WARPS / (NBK / (2 * h));     // fragments per row; warps per pair: 4, 8, 16
+    const int t = warp / wpp, wl = warp % wpp, base = 2 * h * t;
+    const int half = fpr / 2, lo = wl % half, ypw = wpp / half;     // half = 1, 2, 4; ypw = 4
     // T = B * A^-1   (A^-1 lower triangular: k >= column fragment start)
-    for (int f = warp; f < n_pairs * per_pair; f += DIAG_WARPS) {
-      const int t = f / per_pair, fi = (f % per_pair) / fpr, fn = f % fpr, base = 2 * h * t;
-      double c0 = 0.0, c1 = 0.0;
-      frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base, DLD, M + base * DLD + base + 8 * fn, DLD, 8 * fn, h, 1.0, lane);
-      *reinterpret_cast<double2*>(T + (t * h + 8 * fi + r) * TLD + 8 * fn + 2 * c) = make_double2(c0, c1);
-    }
+    for (int fi = wl / half; fi < fpr; fi += ypw)
+      for (int m = 0; m < 2; ++m) {
+        const int fn = m == 0 ? lo : fpr - 1 - lo;
+        double c0 = 0.0, c1 = 0.0;
+        frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base, DLD, M + base * DLD + base + 8 * fn, DLD, 8 * fn, h, 1.0, lane);
+        *reinterpret_cast<double2*>(T + (t * h + 8 * fi + r) * TLD + 8 * fn + 2 * c) = make_double2(c0, c1);
+      }
     __syncthreads();
+    DIAG_STAMP(h == 16 ? 28 : h == 32 ? 30 : 32);
     // X21 = -C^-1 * T  (C^-1 lower triangular: k < row fragment end)
-    for (int f = warp; f < n_pairs * per_pair; f += DIAG_WARPS) {
-      const int t = f / per_pair, fi = (f % per_pair) / fpr, fn = f % fpr, base = 2 * h * t;
-      double c0 = 0.0, c1 = 0.0;
-      frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base + h, DLD, T + (t * h) * TLD + 8 * fn, TLD, 0, 8 * fi + 8, -1.0, lane);
-      *reinterpret_cast<double2*>(M + (base + h + 8 * fi + r) * DLD + base + 8 * fn + 2 * c) = make_double2(c0, c1);
-    }
+    for (int fn = wl / half; fn < fpr; fn += ypw)
+      for (int m = 0; m < 2; ++m) {
+        const int fi = m == 0 ? lo : fpr - 1 - lo;
+        double c0 = 0.0, c1 = 0.0;
+        frag_mac<true>(c0, c1, M + (base + h + 8 * fi) * DLD + base + h, DLD, T + (t * h) * TLD + 8 * fn, TLD, 0, 8 * fi + 8, -1.0, lane);
+        *reinterpret_cast<double2*>(M + (base + h + 8 * fi + r) * DLD + base + 8 * fn + 2 * c) = make_double2(c0, c1);
+      }
     __syncthreads();
+    DIAG_STAMP(h == 16 ? 29 : h == 32 ? 31 : 33);
   }
-  // x_j = inv(L_jj) r_j ; outputs
-  if (tid < NBK) {
+  // x_j = inv(L_jj) r_j : 4 threads per row, k interleaved, fixed shuffle tree
+  {
+    const int row = tid >> 2, part = tid & 3;
     double xv = 0.0;
-    for (int k = 0; k <= tid; ++k) xv = fma(M[tid * DLD + k], rj[k], xv);
-    beta[(long long)s * Np + j * NBK + tid] = xv;
+    for (int k = part; k <= row; k += 4) xv = fma(M[row * DLD + k], rj[k], xv);
+    xv += __shfl_xor_sync(0xffffffffu, xv, 1);
+    xv += __shfl_xor_sync(0xffffffffu, xv, 2);
+    if (part == 0) beta[(long long)s * Np + j * NBK + row] = xv;
   }
+  DIAG_STAMP(34);
+  // the inverse in tiled order, ready to be a GEMM operand: only the pairs on or below the diagonal are written (the
+  // buffer is zeroed once when the handle is created and nothing else writes to it; a single SM stores ~32 bytes per
+  // cycle, so the 64 KB that are always zero would cost as much as the rest).  16 bytes per thread, consecutive
+  // threads consecutive addresses.  The transposes (alpha_kernel, FP64 inversion sweep) are made by one launch for
+  // all block columns after the factorisation (dinv_transpose_kernel).
   double* di = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  double* dt = dinvT + (long long)s * dinv_stride + (long long)j * NBK * NBK;
-  for (int e = tid; e < NBK * NBK; e += DIAG_THREADS) {   // both in tiled order, ready to be GEMM operands
-    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
-    di[e] = (k <= i) ? M[i * DLD + k] : 0.0;
-    dt[e] = (k >= i) ? M[k * DLD + i] : 0.0;
+#pragma unroll 4
+  for (int u = tid; u < NBK * NBK / 2; u += DIAG_THREADS) {
+    const int i = (u >> 1) & 127, k0 = (u >> 10) * TILE_K + ((u >> 8) & 3) * 4 + (u & 1) * 2;
+    if (k0 <= i) {
+      const double2 v = *reinterpret_cast<const double2*>(M + i * DLD + k0);
+      *reinterpret_cast<double2*>(di + 2 * u) = make_double2(v.x, k0 + 1 <= i ? v.y : 0.0);
+    }
   }
   if (tid == 0) {
     double ld_acc = 0.0;
     for (int q = 0; q < NBK; ++q) ld_acc += lg[q];
     logdet[s] = (j == 0 ? 0.0 : logdet[s]) + ld_acc;
+    const int my_info = s_info;
     if (j == 0) info[s] = my_info;
     else if (info[s] == 0 && my_info != 0) info[s] = my_info;
+  }
+  DIAG_STAMP(35);
+}
+
+// dinvT(j) = dinv(j)^T for every block column and draw, tiled order on both sides
+__global__ void dinv_transpose_kernel(const double* __restrict__ dinv, double* __restrict__ dinvT, long long dinv_stride, int s0) {
+  const long long off = (long long)(s0 + blockIdx.y) * dinv_stride + (long long)blockIdx.x * NBK * NBK;
+  const double* di = dinv + off;
+  double* dt = dinvT + off;
+  for (int e = threadIdx.x; e < NBK * NBK; e += blockDim.x) {
+    const int kk = e & 3, i = (e >> 2) & 127, k = (e >> 11) * TILE_K + ((e >> 9) & 3) * 4 + kk;
+    dt[e] = (k >= i) ? di[elem_off(k, i)] : 0.0;
   }
 }
 
@@ -316,6 +465,158 @@ trail_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, in
           make_double2(-acc.c[i][jj][0], -acc.c[i][jj][1]);
 }
 
+// ---- row-sliced variants for one or two factors ----------------------------------------------------
+// With a single factor a block column offers at most 31 tiles: one CTA per tile leaves most SMs idle for the ~17 us a
+// 128 x 128 x 128 product takes on one SM's DMMA pipe, and the k = 512 updates hold an SM for ~70 us while the chain's
+// next kernel waits for a free one.  Here a CTA owns SL_ROWS = 32 rows of a tile (4 CTAs per tile): the B operand
+// streams as whole 16 KB k-tiles, the A operand as the 4 x 1 KB row runs of its k-tile.  Every output element sees the
+// same DMMA sequence (k ascending, one accumulator) and the beta reduction keeps the order of panel_kernel, so the
+// results are bit-identical to the tile kernels.  Warp (wm, wn) owns rows 16 wm.., columns 32 wn.. : 2 x 4 fragments.
+constexpr int SL_ROWS = 32, SL_STAGES = 8, SL_AHEAD = 6;
+constexpr int SL_A_DOUBLES = SL_ROWS * TILE_K;                     // 512
+constexpr int SL_STAGE_DOUBLES = TILE_DOUBLES + SL_A_DOUBLES;      // B tile then A slice: 20 KB
+constexpr int SL_SMEM = SL_STAGES * SL_STAGE_DOUBLES * 8 + 256;    // + 2 * SL_STAGES barriers
+
+struct SliceAcc { double c[2][4][2]; };
+
+struct SliceRing {
+  double* smem;
+  uint64_t *full, *empty;
+  int issued, consumed;
+  __device__ __forceinline__ void init(double* base) {
+    smem = base;
+    full = reinterpret_cast<uint64_t*>(base + SL_STAGES * SL_STAGE_DOUBLES);
+    empty = full + SL_STAGES;
+    issued = consumed = 0;
+    if (threadIdx.x == 0) {
+      for (int st = 0; st < SL_STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, THREADS / 32); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // thread 0: k-tile of B (128 rows) and rows r0 .. r0 + 31 of the matching k-tile of A
+  __device__ __forceinline__ void produce(const double* a_tile, const double* b_tile, int r0) {
+    const int slot = issued % SL_STAGES;
+    if (issued >= SL_STAGES) mbar_wait(empty + slot, (unsigned)(((issued / SL_STAGES) - 1) & 1));
+    double* st = smem + slot * SL_STAGE_DOUBLES;
+    mbar_arrive_expect_tx(full + slot, SL_STAGE_DOUBLES * 8);
+    bulk_g2s(st, b_tile, TILE_DOUBLES * 8, full + slot);
+#pragma unroll
+    for (int g4 = 0; g4 < KG; ++g4)
+      bulk_g2s(st + TILE_DOUBLES + g4 * (SL_ROWS * 4), a_tile + g4 * (BM * 4) + r0 * 4, SL_ROWS * 4 * 8, full + slot);
+    ++issued;
+  }
+};
+
+// acc += A[r0 .. r0+31, :] * B^T over KT consecutive k-tiles
+__device__ __forceinline__ void slice_mainloop(SliceRing& ring, const double* __restrict__ gA, const double* __restrict__ gB, int KT, int r0,
+                                               SliceAcc& acc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
+  int p = 0;
+  if (tid == 0)
+    for (; p < SL_AHEAD && p < KT; ++p) ring.produce(gA + (long long)p * TILE_DOUBLES, gB + (long long)p * TILE_DOUBLES, r0);
+  for (int kt = 0; kt < KT; ++kt) {
+    if (tid == 0 && p < KT) { ring.produce(gA + (long long)p * TILE_DOUBLES, gB + (long long)p * TILE_DOUBLES, r0); ++p; }
+    const int slot = ring.consumed % SL_STAGES;
+    mbar_wait(ring.full + slot, (unsigned)((ring.consumed / SL_STAGES) & 1));
+    const double* sB = ring.smem + slot * SL_STAGE_DOUBLES;
+    const double* sA = sB + TILE_DOUBLES;
+#pragma unroll
+    for (int g4 = 0; g4 < KG; ++g4) {
+      double a[2], b[4];
+      const double* pa = sA + g4 * (SL_ROWS * 4) + (16 * wm) * 4 + lane;
+      const double* pb = sB + g4 * (BN * 4) + (32 * wn) * 4 + lane;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = pa[i * 32];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) b[jj] = pb[jj * 32];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) dmma884(acc.c[i][jj][0], acc.c[i][jj][1], a[i], b[jj]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring.empty + slot);
+    ++ring.consumed;
+  }
+  __syncthreads();   // every stage consumed: the ring memory may be reused by the caller's epilogue
+}
+
+// rows of accumulator fragment (i, jj) of this lane inside the 32-row slice / columns inside the tile
+__device__ __forceinline__ int sl_row(int wm, int i, int lane) { return 16 * wm + 8 * i + (lane >> 2); }
+
+// panel: L21 = A21 * inv(L11)^T and beta_i -= L21 x_j, rows r0 .. r0 + 31 of tile it = j + 1 + blockIdx.y
+__global__ void __launch_bounds__(THREADS, 1)
+panel_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, const double* __restrict__ dinv,
+                   long long dinv_stride, double* __restrict__ beta, int s0) {
+  extern __shared__ __align__(128) double smem[];
+  const int s = s0 + blockIdx.z, it = j + 1 + blockIdx.y, r0 = blockIdx.x * SL_ROWS, KPB = NBK / TILE_K;
+  double* tile = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, it, j * KPB);
+  const double* B = dinv + (long long)s * dinv_stride + (long long)j * NBK * NBK;
+  SliceRing ring; ring.init(smem);
+  SliceAcc acc;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc.c[i][jj][0] = acc.c[i][jj][1] = 0.0;
+  slice_mainloop(ring, tile, B, KPB, r0, acc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
+  const double* xj = beta + (long long)s * Np + j * NBK;
+  double* red = smem;   // [32][4]
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = sl_row(wm, i, lane);
+    double part = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int col = frag_col(wn, jj, lane);
+      *reinterpret_cast<double2*>(tile + elem_off(r0 + row, col)) = make_double2(acc.c[i][jj][0], acc.c[i][jj][1]);
+      part += acc.c[i][jj][0] * xj[col] + acc.c[i][jj][1] * xj[col + 1];
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if ((lane & 3) == 0) red[row * 4 + wn] = part;
+  }
+  __syncthreads();
+  if (tid < SL_ROWS) {
+    double sum = ((red[tid * 4 + 0] + red[tid * 4 + 1]) + red[tid * 4 + 2]) + red[tid * 4 + 3];
+    beta[(long long)s * Np + it * NBK + r0 + tid] -= sum;
+  }
+}
+
+// trailing update: C[it][nt] -= L[it][kb0:kb1] L[nt][kb0:kb1]^T, rows r0 .. r0 + 31 of the tile;
+// it = it0 + blockIdx.x / 4, nt = nt0 + blockIdx.y (tiles above the diagonal exit at once)
+__global__ void __launch_bounds__(THREADS, 1)
+trail_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, int kb1, int it0, int nt0, int s0) {
+  extern __shared__ __align__(128) double smem[];
+  const int it = it0 + (blockIdx.x >> 2), nt = nt0 + blockIdx.y, r0 = (blockIdx.x & 3) * SL_ROWS;
+  if (nt > it) return;
+  const int s = s0 + blockIdx.z, KPB = NBK / TILE_K, KTA = Np / TILE_K;
+  double* base = fac + (long long)s * fac_stride;
+  const double* A = base + tile_off(KTA, it, kb0 * KPB);
+  const double* B = base + tile_off(KTA, nt, kb0 * KPB);
+  double* C = base + tile_off(KTA, it, nt * KPB);
+  SliceRing ring; ring.init(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
+  // as trail_kernel: acc starts at -C, accumulates +A B^T, and C_new = -acc
+  SliceAcc acc;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const double2 v = *reinterpret_cast<const double2*>(C + elem_off(r0 + sl_row(wm, i, lane), frag_col(wn, jj, lane)));
+      acc.c[i][jj][0] = -v.x;
+      acc.c[i][jj][1] = -v.y;
+    }
+  slice_mainloop(ring, A, B, (kb1 - kb0) * KPB, r0, acc);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      *reinterpret_cast<double2*>(C + elem_off(r0 + sl_row(wm, i, lane), frag_col(wn, jj, lane))) =
+          make_double2(-acc.c[i][jj][0], -acc.c[i][jj][1]);
+}
+
 // ---- inversion sweep ------------------------------------------------------------------------------
 __global__ void place_diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, const double* __restrict__ dinv,
                                   long long dinv_stride, int s0) {
@@ -386,6 +687,8 @@ int set_attrs(int device) {
   B7_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
   B7_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   B7_CUDA(cudaFuncSetAttribute(trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+  B7_CUDA(cudaFuncSetAttribute(panel_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
+  B7_CUDA(cudaFuncSetAttribute(trail_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
   B7_CUDA(cudaFuncSetAttribute(inv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   B7_CUDA(cudaFuncSetAttribute(inv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
   g_attr_done[device & 15] = true;
@@ -463,6 +766,44 @@ alpha_kernel(const double* __restrict__ fac, long long fac_stride, int Np, const
     for (int e = tid; e < Np; e += ALPHA_THREADS) alpha[(long long)s * Np + e] = r[e];
 }
 
+// B7_POTRF_TRACE=1: an event after every launch of the main stream; b7_launch_potrf then synchronises and prints the time
+// between consecutive events by kernel (stderr).  Debugging aid for the single-factor latency chain, off by default.
+struct PotrfTrace {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> tag;
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    tag.push_back(name);
+  }
+  void dump() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const char* names[] = {"diag", "panel", "trail", "slice", "near", "wait_far", "transpose"};
+    double sum[7] = {0, 0, 0, 0, 0, 0, 0};
+    int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      for (int k = 0; k < 7; ++k)
+        if (strcmp(tag[i], names[k]) == 0) { sum[k] += ms; ++cnt[k]; }
+      if (getenv("B7_POTRF_TRACE") && atoi(getenv("B7_POTRF_TRACE")) > 1) fprintf(stderr, "  %-10s %8.1f us\n", tag[i], ms * 1e3);
+    }
+    float total = 0.f;
+    if (ev.size() > 1) cudaEventElapsedTime(&total, ev.front(), ev.back());
+    fprintf(stderr, "potrf trace: total %.1f us;", total * 1e3);
+    for (int k = 0; k < 7; ++k)
+      if (cnt[k]) fprintf(stderr, " %s %d x %.1f us;", names[k], cnt[k], sum[k] * 1e3 / cnt[k]);
+    fprintf(stderr, "\n");
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+
 }  // namespace
 
 int b7_launch_potrf(b7_gp* gp, int s0, int count) {
@@ -474,6 +815,10 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   const int W = W_env > 0 ? W_env : 4;   // outer panel = 4 blocks (512 columns)
   cudaStream_t sa = ctx->stream, sb = ctx->stream2;
   bool far_pending = false;
+  PotrfTrace trace;
+  trace.on = getenv("B7_POTRF_TRACE") != nullptr;
+  trace.st = sa;
+  trace.mark("start");
   // INT8 path (potrf_i8.cu): the panel rows are sliced once per outer panel into one of two scratch sets (the far
   // update of panel J still reads its set while panel J + W is sliced)
   // (batched fits only: a single factor is a latency chain that the extra slicing launch makes longer; measured
@@ -483,6 +828,9 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   // The choice looks at the handle's total number of draws, not at how many of them this call factorises: a sharded fit
   // (each GPU factorises S / G draws) then uses the same arithmetic as the one-GPU fit and stays bit-identical to it.
   const int batch = gp->S;
+  // one or two factors: row-sliced kernels (4 CTAs per tile, bit-identical results), see panel_slice_kernel
+  static const int slice_env = getenv("B7_POTRF_SLICE") ? atoi(getenv("B7_POTRF_SLICE")) : -1;
+  const bool sliced = slice_env >= 0 ? slice_env != 0 : count <= 2;
   const bool i8 = ctx->use_i8 && ctx->potrf_i8 && batch >= 4 && (long long)batch * NB * NB >= 4096 && NB > W && Np <= B7_I8_MAX_NP;
   int8_t* pS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   double* pSig[2] = {nullptr, nullptr};
@@ -498,17 +846,23 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
     const int Jend = J + W < NB ? J + W : NB;
     // --- the panel's own columns: latency-bound chain on the main stream ---
     for (int j = J; j < Jend; ++j) {
-      diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, gp->dinvT, ds, gp->beta,
-                                                        gp->logdet, gp->info, s0);
+      diag_kernel<<<count, DIAG_THREADS, DIAG_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, gp->logdet, gp->info, s0);
       b7_count(ctx);
+      trace.mark("diag");
       const int rem = NB - 1 - j;
       if (rem > 0) {
-        panel_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
+        if (sliced) panel_slice_kernel<<<dim3(NBK / SL_ROWS, rem, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
+        else panel_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
         b7_count(ctx);
+        trace.mark("panel");
       }
       if (Jend - 1 - j > 0) {   // columns j+1 .. Jend-1 of the outer panel, all rows below
-        trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
+        if (sliced)
+          trail_slice_kernel<<<dim3(rem * (NBK / SL_ROWS), Jend - 1 - j, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
+        else
+          trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
         b7_count(ctx);
+        trace.mark("trail");
       }
     }
     if (Jend >= NB) break;
@@ -518,19 +872,27 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
     const int near_end = Jend + W < NB ? Jend + W : NB;
     if (i8) B7_CHECK(b7_i8_panel_slice(ctx, sa, gp->fac, Np, J, Jend, Jend, pS[set][0], pS[set][1], p_stride, pSig[set], s0, count));
     if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+    trace.mark("wait_far");
     if (i8) {
       B7_CHECK(b7_i8_trail(ctx, sa, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, Jend, NB - Jend, Jend,
                            near_end - Jend, s0, count));
+    } else if (sliced) {
+      trail_slice_kernel<<<dim3((NB - Jend) * (NBK / SL_ROWS), near_end - Jend, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
+      b7_count(ctx);
     } else {
       trail_kernel<<<dim3(NB - Jend, near_end - Jend, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
       b7_count(ctx);
     }
+    trace.mark("near");
     if (near_end < NB) {
       B7_CUDA(cudaEventRecord(ctx->evA, sa));
       B7_CUDA(cudaStreamWaitEvent(sb, ctx->evA, 0));
       if (i8) {
         B7_CHECK(b7_i8_trail(ctx, sb, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, near_end, NB - near_end,
                              near_end, NB - near_end, s0, count));
+      } else if (sliced) {
+        trail_slice_kernel<<<dim3((NB - near_end) * (NBK / SL_ROWS), NB - near_end, count), THREADS, SL_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
+        b7_count(ctx);
       } else {
         trail_kernel<<<dim3(NB - near_end, NB - near_end, count), THREADS, RING_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
         b7_count(ctx);
@@ -541,6 +903,11 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
     set ^= 1;
   }
   if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+  trace.mark("wait_far");
+  dinv_transpose_kernel<<<dim3(NB, count), 512, 0, sa>>>(gp->dinv, gp->dinvT, ds, s0);
+  b7_count(ctx);
+  trace.mark("transpose");
+  trace.dump();
   if (i8)
     for (int b = 0; b < 2; ++b) {
       b7_pool_free(ctx, pS[b][0]);

@@ -473,6 +473,29 @@ def test_int8_path_at_its_largest_size_matches_the_fp64_path(ctx, oracle):
         assert e["mean"] <= max(1e-9, 4 * oracle_err), report
 
 
+@pytest.mark.parametrize("N", [300, 1100, 2304])
+def test_one_factor_latency_path_gives_the_bits_of_the_batched_fit(ctx, oracle, N):
+    # potrf.cu: one or two factors per call run the row-sliced panel / trailing kernels (4 CTAs per tile); three use the
+    # tile kernels.  Same DMMA sequence per element, same reduction order for beta: factor, log marginal likelihood and
+    # beta-dependent results must be bit-identical.  FP64 path on both sides (three draws never take the INT8 updates).
+    Xo, y, hyp, _ = make_problem(oracle, N, 6, 3, 10, 1e-3)
+    keep = ctx.posterior_path()
+    try:
+        ctx.set_posterior_path(L.PATH_FP64_DMMA)
+        three = models.GPFactors(Xo, y, hyp, flags=L.FIT_LOGML_ONLY)
+        one = models.GPFactors(Xo, y, hyp[1:2], flags=L.FIT_LOGML_ONLY)
+        assert (np.asarray(three.info) == 0).all() and (np.asarray(one.info) == 0).all()
+        assert np.array_equal(one.logml, three.logml[1:2])
+        assert np.array_equal(one.read_factor(0), three.read_factor(1))
+        ref = oracle.gp_fit(Xo, y, hyp[1], 0)
+        assert np.max(np.abs(one.read_factor(0) - np.tril(ref["L"]))) <= 1e-10 * np.max(np.abs(ref["L"]))
+        assert rel(np.asarray(one.logml), np.array([ref["logml"]]), 1e-300) <= 1e-11
+        one.free()
+        three.free()
+    finally:
+        ctx.set_posterior_path(keep)
+
+
 def test_fit_is_deterministic_and_predict_needs_inverse(ctx, oracle):
     Xo, y, hyp, Xc = make_problem(oracle, 300, 6, 3, 2000, 1e-2)
     a = models.GPFactors(Xo, y, hyp)
