@@ -227,6 +227,9 @@ int b7_init(int device, b7_ctx** out) {
   B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evA, cudaEventDisableTiming));
   B7_CUDA(cudaEventCreateWithFlags(&ctx->evB, cudaEventDisableTiming));
+  B7_CUDA(cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, (prio_hi + prio_lo) / 2));
+  B7_CUDA(cudaEventCreateWithFlags(&ctx->evS, cudaEventDisableTiming));
+  B7_CUDA(cudaEventCreateWithFlags(&ctx->evS1, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     B7_CUDA(cudaEventCreateWithFlags(&ctx->evK[i], cudaEventDisableTiming));
     B7_CUDA(cudaEventCreateWithFlags(&ctx->evP[i], cudaEventDisableTiming));
@@ -273,6 +276,10 @@ void b7_shutdown(b7_ctx* ctx) {
   cache_flush(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->stream2);
+  cudaStreamSynchronize(ctx->stream3);
+  cudaEventDestroy(ctx->evS);
+  cudaEventDestroy(ctx->evS1);
+  cudaStreamDestroy(ctx->stream3);
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->evK[i]); cudaEventDestroy(ctx->evP[i]); }
@@ -445,6 +452,7 @@ void b7_gp_free(b7_gp* gp) {
   cudaStreamSynchronize(gp->ctx->stream);
   void* ptrs[] = {gp->X, gp->Xt, gp->y, gp->par, gp->fac, gp->facS, gp->sigma, gp->dinv, gp->dinvT, gp->beta, gp->alpha, gp->tt, gp->logdet, gp->info, gp->meta_dev};
   for (void* p : ptrs) dev_free(gp->ctx, p);
+  if (gp->potrf_graph) cudaGraphExecDestroy(gp->potrf_graph);
   delete gp;
 }
 

@@ -37,7 +37,8 @@ struct b7_ctx {
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;                   // private stream-ordered pool: the device's default pool is left alone
   cudaStream_t stream2 = nullptr;                 // far trailing updates of the Cholesky (overlaps the next panel)
-  cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaStream_t stream3 = nullptr;                 // single-factor Cholesky: updates of the columns that are not needed next
+  cudaEvent_t evA = nullptr, evB = nullptr, evS = nullptr, evS1 = nullptr;
   cudaEvent_t evK[2] = {nullptr, nullptr}, evP[2] = {nullptr, nullptr};   // K* pass of draw s + 1 under the posterior pass of draw s
   bool kstar_overlap = true;     // B7_KSTAR_OVERLAP=0: K* and posterior strictly one after the other
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
@@ -103,6 +104,10 @@ struct b7_gp {
   double* logdet = nullptr; // device S : sum log L_ii
   int* info = nullptr;      // device S
   double* meta_dev = nullptr;   // device S x 3 : (info, log ml, jitter) per draw, exchanged by the sharded fit
+  // single-factor Cholesky replayed as a CUDA graph from the second call with the same (first draw, count) on
+  // (the slice sampler's density evaluations: same handle, new hyper-parameters in device memory)
+  cudaGraphExec_t potrf_graph = nullptr;
+  int potrf_graph_s0 = -1, potrf_graph_count = 0, potrf_graph_launches = 0, potrf_calls_s0 = -1, potrf_calls_count = 0, potrf_calls = 0;
   bool fac_complete = true;     // fac holds L^-1 of every draw (false after a sharded fit that exchanged the int8 slices only)
   std::vector<char> sliced;   // per draw: facS/sigma hold the slices of the current L^-1
   std::vector<double> jitter;

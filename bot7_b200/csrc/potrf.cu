@@ -85,6 +85,13 @@ __device__ long long b7_diag_stamps[128];
 //     for h = 16, 32, 64 as fragment products, in place, fragments dealt so that every warp gets the same k length.
 // History (tools/diag_probe.cu, cycles): 152 k with a lane-0 branch per column, float seed + 3 Newton steps, a separate
 // inverse of the piece and no look-ahead (factor 79 k, inverse 18 k, updates 17 k, doubling 18 k, I/O 16 k).
+// Programmatic dependent launch (single-factor schedule): a kernel launched with the programmatic-serialisation
+// attribute may become resident once its stream predecessor has executed pdl_trigger() in every CTA; it must not touch
+// global memory before pdl_wait(), which returns when the predecessor has completed and its writes are visible.
+// Both are no-ops in a kernel that was launched without the attribute / has no dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int BAR_S1 = 1, BAR_U = 2, BAR_S2 = 3;
 constexpr int UPD_THREADS = (DIAG_WARPS - DIAG_WARPS / 4) * 32;   // warps with (warp & 3) != 0
 __device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -199,6 +206,7 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
   const int s = s0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = lane >> 2, c = lane & 3;
   DIAG_STAMP(0);
+  pdl_wait();
   double* blk = fac + (long long)s * fac_stride + tile_off(Np / TILE_K, j, j * (NBK / TILE_K));   // 8 tiles of block (j, j)
 #pragma unroll 8
   for (int u = tid; u < NBK * NBK / 2; u += DIAG_THREADS) {
@@ -346,6 +354,9 @@ diag_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, doubl
     __syncthreads();
     DIAG_STAMP(h == 16 ? 29 : h == 32 ? 31 : 33);
   }
+  // the panel kernel's CTAs may take their SMs now (not earlier: they would sit on 124 SMs that the side and far streams
+  // use while this block is factored)
+  pdl_trigger();
   // x_j = inv(L_jj) r_j : 4 threads per row, k interleaved, fixed shuffle tree
   {
     const int row = tid >> 2, part = tid & 3;
@@ -559,6 +570,8 @@ panel_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) acc.c[i][jj][0] = acc.c[i][jj][1] = 0.0;
+  pdl_trigger();
+  pdl_wait();
   slice_mainloop(ring, tile, B, KPB, r0, acc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
   const double* xj = beta + (long long)s * Np + j * NBK;
@@ -590,13 +603,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 trail_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, int kb1, int it0, int nt0, int s0) {
   extern __shared__ __align__(128) double smem[];
   const int it = it0 + (blockIdx.x >> 2), nt = nt0 + blockIdx.y, r0 = (blockIdx.x & 3) * SL_ROWS;
-  if (nt > it) return;
+  pdl_trigger();
+  if (nt > it) { pdl_wait(); return; }     // (a CTA that left without waiting would let the grid complete before its predecessor)
   const int s = s0 + blockIdx.z, KPB = NBK / TILE_K, KTA = Np / TILE_K;
   double* base = fac + (long long)s * fac_stride;
   const double* A = base + tile_off(KTA, it, kb0 * KPB);
   const double* B = base + tile_off(KTA, nt, kb0 * KPB);
   double* C = base + tile_off(KTA, it, nt * KPB);
   SliceRing ring; ring.init(smem);
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3;
   // as trail_kernel: acc starts at -C, accumulates +A B^T, and C_new = -acc
   SliceAcc acc;
@@ -684,13 +699,21 @@ __global__ void untile_kernel(const double* __restrict__ facT, double* __restric
 bool g_attr_done[16] = {false};   // function attributes are per device
 int set_attrs(int device) {
   if (g_attr_done[device & 15]) return 0;
-  B7_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(trail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(panel_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(trail_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(inv_step1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
-  B7_CUDA(cudaFuncSetAttribute(inv_step2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM));
+  // every kernel of the chain asks for the same (largest) shared-memory carve-out: consecutive kernels with different
+  // carve-outs make the SMs reconfigure between launches, which shows up as microseconds of gap in a chain of ~100
+  // dependent launches
+  auto set = [](const void* fn, int smem) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  };
+  B7_CUDA(set((const void*)diag_kernel, DIAG_SMEM));
+  B7_CUDA(set((const void*)panel_kernel, RING_SMEM));
+  B7_CUDA(set((const void*)trail_kernel, RING_SMEM));
+  B7_CUDA(set((const void*)panel_slice_kernel, SL_SMEM));
+  B7_CUDA(set((const void*)trail_slice_kernel, SL_SMEM));
+  B7_CUDA(set((const void*)inv_step1_kernel, RING_SMEM));
+  B7_CUDA(set((const void*)inv_step2_kernel, RING_SMEM));
   g_attr_done[device & 15] = true;
   return 0;
 }
@@ -804,6 +827,176 @@ struct PotrfTrace {
   }
 };
 
+// One or two factors: every kernel of the chain diag -> panel -> update of the next column is on the critical path of
+// the whole fit (32 block columns at N = 4096), and the machine is otherwise empty.  Same operations on every tile in
+// the same order as the batched schedule below (results are bit-identical), but
+//   * panel and trailing updates run row-sliced (4 CTAs per tile: ~5 us instead of ~20 us per wave);
+//   * on the main stream a column step only updates the NEXT column; the other columns of the outer panel get the same
+//     update on a side stream while the next diagonal block is factored (they are needed one step later each);
+//   * after an outer panel only the first column of the next one gets its k = 512 update on the main stream, the other
+//     columns follow on the side stream, everything further right on the far stream as in the batched schedule.
+int potrf_latency_enqueue(b7_gp* gp, int s0, int count, int W, bool allow_trace);
+
+// The schedule above is ~100 dependent launches and as many event operations: enqueued one by one the host is not
+// always ahead of the GPU and every dependent launch costs microseconds of gap.  A handle that is factorised again with
+// the same (first draw, count) -- b7_gp_refit, i.e. every density evaluation of the slice sampler -- captures the
+// schedule into a CUDA graph once (all kernel arguments are per-handle constants; the hyper-parameters live in device
+// memory) and replays it from then on.  Measured (tools/fit_latency.py, refit ms with / without the graph): N = 2048
+// 0.86 / 0.90, N = 4096 2.17 / 2.03, N = 8192 9.64 / 9.01 -- the replay wins while the chain is short and loses once the
+// far updates are large (their nodes and the chain's are scheduled on equal terms whatever the node priorities say), so
+// the graph is used up to 16 block columns.  B7_POTRF_GRAPH=0 disables it, =1 forces it at every size.
+int potrf_latency(b7_gp* gp, int s0, int count, int W) {
+  b7_ctx* ctx = gp->ctx;
+  static const int graph_env = getenv("B7_POTRF_GRAPH") ? atoi(getenv("B7_POTRF_GRAPH")) : -1;
+  const bool graph_ok = graph_env >= 0 ? graph_env != 0 : gp->NB <= 16;
+  if (!graph_ok || getenv("B7_POTRF_TRACE")) return potrf_latency_enqueue(gp, s0, count, W, true);
+  if (gp->potrf_graph && gp->potrf_graph_s0 == s0 && gp->potrf_graph_count == count) {
+    B7_CUDA(cudaGraphLaunch(gp->potrf_graph, ctx->stream));
+    b7_count(ctx, gp->potrf_graph_launches);
+    return 0;
+  }
+  if (gp->potrf_calls_s0 == s0 && gp->potrf_calls_count == count) ++gp->potrf_calls;
+  else { gp->potrf_calls_s0 = s0; gp->potrf_calls_count = count; gp->potrf_calls = 1; }
+  if (gp->potrf_calls < 2) return potrf_latency_enqueue(gp, s0, count, W, false);
+  // second call with this key: capture, instantiate, launch
+  if (gp->potrf_graph) { cudaGraphExecDestroy(gp->potrf_graph); gp->potrf_graph = nullptr; }
+  const int64_t before = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  B7_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = potrf_latency_enqueue(gp, s0, count, W, false);
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != 0 || e != cudaSuccess || graph == nullptr) {
+    if (getenv("B7_DEBUG")) fprintf(stderr, "potrf graph: capture failed (rc %d, %s)\n", rc, cudaGetErrorString(e));
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->launches = before;
+    gp->potrf_calls = -(1 << 30);            // do not try again on this handle
+    return potrf_latency_enqueue(gp, s0, count, W, false);
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&gp->potrf_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) {
+    if (getenv("B7_DEBUG")) fprintf(stderr, "potrf graph: instantiation failed (%s)\n", cudaGetErrorString(ei));
+    gp->potrf_graph = nullptr;
+    cudaGetLastError();
+    ctx->launches = before;
+    gp->potrf_calls = -(1 << 30);
+    return potrf_latency_enqueue(gp, s0, count, W, false);
+  }
+  gp->potrf_graph_s0 = s0;
+  gp->potrf_graph_count = count;
+  gp->potrf_graph_launches = (int)(ctx->launches - before);
+  if (getenv("B7_DEBUG")) fprintf(stderr, "potrf graph: %d kernel nodes captured\n", gp->potrf_graph_launches);
+  B7_CUDA(cudaGraphLaunch(gp->potrf_graph, ctx->stream));
+  return 0;
+}
+
+// launch with the programmatic-serialisation attribute (see pdl_wait)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  // the stream's priority as a launch attribute as well: a captured graph keeps it per kernel node (without it the far
+  // update's nodes compete with the chain's on equal terms: N = 8192 9.0 -> 10.0 ms)
+  int prio = 0;
+  cudaStreamGetPriority(st, &prio);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = prio;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+int potrf_latency_enqueue(b7_gp* gp, int s0, int count, int W, bool allow_trace) {
+  b7_ctx* ctx = gp->ctx;
+  static const bool pdl = !(getenv("B7_POTRF_PDL") && atoi(getenv("B7_POTRF_PDL")) == 0);
+  const int Np = gp->Np, NB = gp->NB, SPT = NBK / SL_ROWS;
+  const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK;
+  cudaStream_t sa = ctx->stream, sb = ctx->stream2, sc = ctx->stream3;
+  bool far_pending = false, side_pending = false, near1_pending = false;
+  PotrfTrace trace;
+  trace.on = allow_trace && getenv("B7_POTRF_TRACE") != nullptr;
+  trace.st = sa;
+  trace.mark("start");
+  // kernels of the main stream follow their predecessor programmatically; the side and far streams launch normally
+  auto trail = [&](cudaStream_t st, int kb0, int kb1, int it0, int n_it, int nt0, int n_nt) {
+    launch_pdl(trail_slice_kernel, dim3(n_it * SPT, n_nt, count), dim3(THREADS), SL_SMEM, st, pdl && st == sa, gp->fac, fs, Np, kb0, kb1, it0, nt0, s0);
+    b7_count(ctx);
+  };
+  for (int J = 0; J < NB; J += W) {
+    const int Jend = J + W < NB ? J + W : NB;
+    for (int j = J; j < Jend; ++j) {
+      launch_pdl(diag_kernel, dim3(count), dim3(DIAG_THREADS), DIAG_SMEM, sa, pdl && j > 0, gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, gp->logdet,
+                 gp->info, s0);
+      b7_count(ctx);
+      trace.mark("diag");
+      const int rem = NB - 1 - j;
+      if (rem > 0) {
+        launch_pdl(panel_slice_kernel, dim3(SPT, rem, count), dim3(THREADS), SL_SMEM, sa, pdl, gp->fac, fs, Np, j, (const double*)gp->dinv, ds, gp->beta, s0);
+        b7_count(ctx);
+        trace.mark("panel");
+      }
+      if (j + 1 < Jend) {
+        // column j + 1 <- column j, after whatever the side stream still had to do to that column
+        if (near1_pending) { B7_CUDA(cudaStreamWaitEvent(sa, ctx->evS1, 0)); near1_pending = false; }
+        // (at the first step of a panel the side stream may still be busy with the k = 128 W update of columns >= J + 2:
+        //  not needed here, and ordered before this step's side launch by the stream itself)
+        if (side_pending && j > J) { B7_CUDA(cudaStreamWaitEvent(sa, ctx->evS, 0)); side_pending = false; }
+        trail(sa, j, j + 1, j + 1, rem, j + 1, 1);
+        trace.mark("trail");
+        if (j + 2 < Jend) {   // columns j + 2 .. Jend - 1 <- column j on the side stream (rows from j + 2: the lower tiles)
+          B7_CUDA(cudaEventRecord(ctx->evA, sa));
+          B7_CUDA(cudaStreamWaitEvent(sc, ctx->evA, 0));
+          trail(sc, j, j + 1, j + 2, rem - 1, j + 2, Jend - 2 - j);
+          B7_CUDA(cudaEventRecord(ctx->evS, sc));
+          side_pending = true;
+        }
+      }
+    }
+    if (Jend >= NB) break;
+    const int near_end = Jend + W < NB ? Jend + W : NB;
+    if (side_pending) { B7_CUDA(cudaStreamWaitEvent(sa, ctx->evS, 0)); side_pending = false; }
+    if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));     // it touched the next panel's tiles
+    trace.mark("wait_far");
+    trail(sa, J, Jend, Jend, NB - Jend, Jend, 1);                        // first column of the next panel, k = 128 W
+    trace.mark("near");
+    B7_CUDA(cudaEventRecord(ctx->evA, sa));
+    if (near_end - Jend > 1) {
+      B7_CUDA(cudaStreamWaitEvent(sc, ctx->evA, 0));
+      trail(sc, J, Jend, Jend + 1, NB - Jend - 1, Jend + 1, 1);         // its second column: needed one step later
+      B7_CUDA(cudaEventRecord(ctx->evS1, sc));
+      near1_pending = true;
+      if (near_end - Jend > 2) {
+        trail(sc, J, Jend, Jend + 2, NB - Jend - 2, Jend + 2, near_end - Jend - 2);
+        B7_CUDA(cudaEventRecord(ctx->evS, sc));
+        side_pending = true;
+      }
+    }
+    if (near_end < NB) {
+      B7_CUDA(cudaStreamWaitEvent(sb, ctx->evA, 0));
+      trail(sb, J, Jend, near_end, NB - near_end, near_end, NB - near_end);
+      B7_CUDA(cudaEventRecord(ctx->evB, sb));
+      far_pending = true;
+    }
+  }
+  if (far_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evB, 0));
+  if (side_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evS, 0));
+  if (near1_pending) B7_CUDA(cudaStreamWaitEvent(sa, ctx->evS1, 0));
+  trace.mark("wait_far");
+  dinv_transpose_kernel<<<dim3(NB, count), 512, 0, sa>>>(gp->dinv, gp->dinvT, ds, s0);
+  b7_count(ctx);
+  trace.mark("transpose");
+  trace.dump();
+  B7_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 int b7_launch_potrf(b7_gp* gp, int s0, int count) {
@@ -813,6 +1006,9 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   const long long fs = (long long)Np * Np, ds = (long long)NB * NBK * NBK;
   static const int W_env = getenv("B7_POTRF_W") ? atoi(getenv("B7_POTRF_W")) : 0;
   const int W = W_env > 0 ? W_env : 4;   // outer panel = 4 blocks (512 columns)
+  // one or two factors: the latency-oriented schedule with row-sliced kernels (bit-identical results)
+  static const int slice_env = getenv("B7_POTRF_SLICE") ? atoi(getenv("B7_POTRF_SLICE")) : -1;
+  if (slice_env >= 0 ? slice_env != 0 : count <= 2) return potrf_latency(gp, s0, count, W);
   cudaStream_t sa = ctx->stream, sb = ctx->stream2;
   bool far_pending = false;
   PotrfTrace trace;
@@ -828,9 +1024,6 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   // The choice looks at the handle's total number of draws, not at how many of them this call factorises: a sharded fit
   // (each GPU factorises S / G draws) then uses the same arithmetic as the one-GPU fit and stays bit-identical to it.
   const int batch = gp->S;
-  // one or two factors: row-sliced kernels (4 CTAs per tile, bit-identical results), see panel_slice_kernel
-  static const int slice_env = getenv("B7_POTRF_SLICE") ? atoi(getenv("B7_POTRF_SLICE")) : -1;
-  const bool sliced = slice_env >= 0 ? slice_env != 0 : count <= 2;
   const bool i8 = ctx->use_i8 && ctx->potrf_i8 && batch >= 4 && (long long)batch * NB * NB >= 4096 && NB > W && Np <= B7_I8_MAX_NP;
   int8_t* pS[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   double* pSig[2] = {nullptr, nullptr};
@@ -851,16 +1044,12 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
       trace.mark("diag");
       const int rem = NB - 1 - j;
       if (rem > 0) {
-        if (sliced) panel_slice_kernel<<<dim3(NBK / SL_ROWS, rem, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
-        else panel_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
+        panel_kernel<<<dim3(rem, 1, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, gp->dinv, ds, gp->beta, s0);
         b7_count(ctx);
         trace.mark("panel");
       }
       if (Jend - 1 - j > 0) {   // columns j+1 .. Jend-1 of the outer panel, all rows below
-        if (sliced)
-          trail_slice_kernel<<<dim3(rem * (NBK / SL_ROWS), Jend - 1 - j, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
-        else
-          trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
+        trail_kernel<<<dim3(rem, Jend - 1 - j, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, j, j + 1, j + 1, j + 1, s0);
         b7_count(ctx);
         trace.mark("trail");
       }
@@ -876,9 +1065,6 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
     if (i8) {
       B7_CHECK(b7_i8_trail(ctx, sa, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, Jend, NB - Jend, Jend,
                            near_end - Jend, s0, count));
-    } else if (sliced) {
-      trail_slice_kernel<<<dim3((NB - Jend) * (NBK / SL_ROWS), near_end - Jend, count), THREADS, SL_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
-      b7_count(ctx);
     } else {
       trail_kernel<<<dim3(NB - Jend, near_end - Jend, count), THREADS, RING_SMEM, sa>>>(gp->fac, fs, Np, J, Jend, Jend, Jend, s0);
       b7_count(ctx);
@@ -890,9 +1076,6 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
       if (i8) {
         B7_CHECK(b7_i8_trail(ctx, sb, gp->fac, Np, pS[set][0], pS[set][1], p_stride, pSig[set], J, Jend, Jend, near_end, NB - near_end,
                              near_end, NB - near_end, s0, count));
-      } else if (sliced) {
-        trail_slice_kernel<<<dim3((NB - near_end) * (NBK / SL_ROWS), NB - near_end, count), THREADS, SL_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
-        b7_count(ctx);
       } else {
         trail_kernel<<<dim3(NB - near_end, NB - near_end, count), THREADS, RING_SMEM, sb>>>(gp->fac, fs, Np, J, Jend, near_end, near_end, s0);
         b7_count(ctx);
