@@ -12,7 +12,9 @@ step   : headline / c2 / c4 (weak scaling, factors and grid resident): one pass 
 value  : whole-job candidates/s, inputs resident in HBM when the timed region starts (device time between two CUDA
          events on the library's stream, max over ranks).
 e2e    : the same through the C ABI with HOST buffers: b7_gp_fit_sharded (X, y, hyp from the host), the candidate batch
-         uploaded with b7_grid_from_host_sharded, b7_acq_score_multi with the score vector read back.
+         uploaded with b7_grid_from_host_sharded, b7_acq_score_multi with the score vector read back.  Headline: one
+         acquisition over 2^20 candidates per GPU (the survey's headline shape); the same with a batch the size
+         of the timed step is reported beside it as e2e_step_batch.
 multi  : one process per GPU (torchrun); everything that crosses GPUs runs inside libbot7_b200.so (b7_comm_init_rank,
          b7_gp_fit_sharded, b7_acq_score_multi: NCCL over NVLink); torch.distributed (gloo) only carries the 128-byte
          NCCL id, the barriers and the max over ranks of the timings.
@@ -279,7 +281,7 @@ def main():
     ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
     ap.add_argument("--candidates", type=int, default=None, help="override the config's candidate count (per GPU if weak, total if strong)")
-    ap.add_argument("--e2e-candidates", type=int, default=None, help="candidates per GPU of the end-to-end leg (default: the step's)")
+    ap.add_argument("--e2e-candidates", type=int, default=None, help="candidates per GPU of the end-to-end leg (default: 2^20 at the headline, else the step's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-path", action="store_true", help="skip the FP64 DMMA path that the 1-GPU headline run times beside the default one")
     args = ap.parse_args()
@@ -434,24 +436,43 @@ def main():
     value = M_total / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (fit + upload + score + read back) ------
-    m_e2e = args.e2e_candidates or (cnt if not strong else min(cnt, 1 << 20))
-    m_e2e = min(m_e2e, cnt)
-    Xc_host = grids_[0].read(0, m_e2e)
-    Xc_all = np.concatenate([Xc_host] * world) if world > 1 else Xc_host   # every rank uploads its own m_e2e rows
-    e2e_times = []
-    for i in range(5):
-        barrier()
-        t0 = time.perf_counter()
-        g2 = comm.grid_from_host(Xc_all)
-        gp2 = comm.fit(Xo, y, hyp)[0]
-        b_, a_, ao_, n_, sc = comm.acq_score(gp2, g2, kind, tradeoff, 0, -1.0, fmin, want_scores=True)
-        e2e_times.append(time.perf_counter() - t0)
-        comm.free_fit(gp2)
-        for g in g2:
-            g.free()
-    e2e_s = allmax(float(np.median(e2e_times[2:])))[0]
-    h2d = Xc_host.nbytes + Xo.nbytes + y.nbytes + hyp.nbytes
-    d2h = m_e2e * 8 + 32
+    # headline: the survey's shape, 2^20 candidates per GPU and acquisition; the step-sized batch beside it
+    def e2e_leg(m):
+        if m <= cnt:
+            Xc_host = grids_[0].read(0, m)
+        else:                              # more rows than the resident shard holds: this rank's next m Sobol points, made on the host side
+            Xc_host = np.empty((m, d))
+            L.check(lib.b7_sobol_generate(ctx.handle, d, 1 + N + row0, m, None, None, L.dptr(Xc_host), None), "b7_sobol_generate")
+        Xc_all = np.concatenate([Xc_host] * world) if world > 1 else Xc_host   # every rank uploads its own m rows
+        untimed = 1 if m >= (1 << 19) else 2
+        times = []
+        for i in range(untimed + 3):
+            barrier()
+            t0 = time.perf_counter()
+            g2 = comm.grid_from_host(Xc_all)
+            gp2 = comm.fit(Xo, y, hyp)[0]
+            b_, a_, ao_, n_, sc = comm.acq_score(gp2, g2, kind, tradeoff, 0, -1.0, fmin, want_scores=True)
+            times.append(time.perf_counter() - t0)
+            comm.free_fit(gp2)
+            for g in g2:
+                g.free()
+        sec = allmax(float(np.median(times[untimed:])))[0]
+        return {"value": world * m / sec, "unit": UNIT, "h2d_bytes_per_step": int(Xc_host.nbytes + Xo.nbytes + y.nbytes + hyp.nbytes),
+                "d2h_bytes_per_step": int(m * 8 + 32), "candidates_per_gpu": int(m),
+                "includes": "b7_gp_fit_sharded from host X/y/hyp (K build, batched potrf, inversion, exchange) + b7_grid_from_host_sharded + "
+                            f"b7_acq_score_multi with the score vector copied back; median of 3 steps after {untimed} untimed",
+                "seconds_per_step": sec, "all_steps_s": [round(x, 4) for x in times]}
+
+    if args.e2e_candidates:
+        m_e2e = args.e2e_candidates
+    elif args.config == "headline" and not args.candidates:
+        m_e2e = 1 << 20
+    else:
+        m_e2e = cnt if not strong else min(cnt, 1 << 20)
+    if strong:
+        m_e2e = min(m_e2e, cnt)
+    e2e = e2e_leg(m_e2e)
+    e2e_step_batch = e2e_leg(cnt) if (m_e2e != cnt and not strong) else None
 
     if rank != 0:
         comm.free_fit(state["gps"])
@@ -533,16 +554,14 @@ def main():
         "gp_fit_ms": {"k_build_plus_cholesky": fit_ms["kbuild_ms"] + fit_ms["potrf_ms"], "draws_on_this_rank": own,
                       "per_factor": (fit_ms["kbuild_ms"] + fit_ms["potrf_ms"]) / max(own, 1),
                       "inversion_for_predict": fit_ms["trtri_ms"], **{k: v for k, v in fit_ms.items() if k.endswith("_ms")}},
-        "e2e": {"value": world * m_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "candidates_per_gpu": int(m_e2e),
-                "includes": "b7_gp_fit_sharded from host X/y/hyp (K build, batched potrf, inversion, exchange) + b7_grid_from_host_sharded + "
-                            "b7_acq_score_multi with the score vector copied back; median of 3 steps after 2 untimed ones",
-                "seconds_per_step": e2e_s, "all_steps_s": [round(x, 4) for x in e2e_times]},
+        "e2e": e2e,
         "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,
         "clocks": clocks, "roofline": roofline, "stages": stages, "peaks": pk,
         "posterior_path": path_name[default_path],
         "result": {"best": res[0], "global_index": res[1], "nan_count": res[2]},
     }
+    if e2e_step_batch:
+        line["e2e_step_batch"] = e2e_step_batch
     if other:
         o_ms, o_launches, o_clk, o_res, o_st = other
         line["other_path"] = {"posterior_path": path_name[other_path], "value": M_total / (o_ms * 1e-3), "unit": UNIT, "ms_per_step": o_ms,

@@ -482,10 +482,14 @@ posterior_i8_pair_kernel(const int8_t* __restrict__ facS, const double* __restri
                 bulk_g2s(st, facS, A_STAGE, full + slot);
                 bulk_g2s(st + A_STAGE, ksS, B_HALF, full + slot);
               } else {
-                const int hint = dbg >> 4;      // measurement knob: 1 = L^-1 evict_last, 2 = + K* evict_first, 3 = K* evict_first only
+                // measurement knob: 1 = L^-1 evict_last, 2 = + K* evict_first, 3 = K* evict_first only,
+                //                   4 = L^-1 evict_first + K* evict_last, 5 = L^-1 evict_first only, 6 = K* evict_last only
+                const int hint = dbg >> 4;
                 if (hint == 1 || hint == 2) bulk_g2s_hint(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot, pol_last);
+                else if (hint == 4 || hint == 5) bulk_g2s_hint(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot, pol_first);
                 else bulk_g2s(st, gA + (long long)ks * A_STAGE, A_STAGE, full + slot);
                 if (hint == 2 || hint == 3) bulk_g2s_hint(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot, pol_first);
+                else if (hint == 4 || hint == 6) bulk_g2s_hint(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot, pol_last);
                 else bulk_g2s(st + A_STAGE, gB + (long long)ks * (2 * B_HALF), B_HALF, full + slot);
               }
             }

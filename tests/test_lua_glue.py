@@ -108,3 +108,95 @@ def test_block_keywords_balance(name):
     ends = len(re.findall(r"\bend\b", text))
     assert opens == ends, f"{name}: {opens} block openers vs {ends} `end`"
     assert text.count("(") == text.count(")") and text.count("{") == text.count("}")
+
+
+# ---- full-grammar checks (tools/lua_check.py: Lua 5.1 / LuaJIT lexer + parser + scope resolution) ------------------
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import lua_check  # noqa: E402
+
+GLUE_FILES = sorted(f for f in os.listdir(LUA) if f.endswith(".lua"))
+
+
+@pytest.mark.parametrize("name", GLUE_FILES)
+def test_glue_parses_and_every_name_resolves(name):
+    """The whole file is valid Lua 5.1 and every name it reads is a local in scope or a global that a `th` process provides:
+    a misspelt local or a forgotten `local` would surface here as an unknown global."""
+    rep = lua_check.check_file(os.path.join(LUA, name))
+    assert not lua_check.unknown_globals(rep), f"{name}: unknown globals {lua_check.unknown_globals(rep)}"
+    assert not rep.global_writes, f"{name}: assigns globals {rep.global_writes} (the glue must not leak names into _G)"
+
+
+@pytest.mark.parametrize("name", GLUE_FILES)
+def test_self_method_calls_resolve(name):
+    """`self:m(...)` inside a glue class: m is defined by the class itself, or by the reference parent it subclasses."""
+    text = lua(name)
+    rep = lua_check.check_text(text, name)
+    own = {path.split(":")[1] for path, _ in rep.functions if ":" in path} | \
+          {path.split(".")[-1] for path, _ in rep.functions if "." in path}
+    # methods of the reference parents that the glue relies on (bots/abstract.lua, grids/abstract.lua, models/abstract.lua,
+    # models/dngo.lua, scores/abstract.lua); extracted from the reference when it is present, else this committed list
+    parents = {"bayesopt.lua": ["bots/bayesopt.lua", "bots/abstract.lua"], "grids_sobol.lua": ["grids/sobol.lua", "grids/abstract.lua"],
+               "models_dngo.lua": ["models/dngo.lua", "models/abstract.lua"], "models_gp.lua": ["models/abstract.lua"],
+               "scores.lua": ["scores/abstract.lua"]}
+    committed = {"__init", "cache", "class", "init", "predict", "report", "update", "eval", "nominate", "run_experiment", "generate",
+                 "create_bank", "i4_sobol", "fantasize", "parse_hypers", "sample_hypers", "network", "train", "extract_features"}
+    inherited = set(committed)
+    if os.path.isdir(REF):
+        inherited = set()
+        for f in parents.get(name, []):
+            p = os.path.join(REF, f)
+            if os.path.exists(p):
+                r = lua_check.check_file(p)
+                inherited |= {path.split(":")[1] for path, _ in r.functions if ":" in path}
+                inherited |= {path.split(".")[-1] for path, _ in r.functions if "." in path}
+    for obj, m, line in rep.method_calls:
+        if obj == "self":
+            assert m in own or m in inherited, f"{name}:{line}: self:{m}() is defined neither here nor in {parents.get(name)}"
+
+
+def test_checker_parses_the_whole_reference_tree():
+    """Validation of the checker itself: all of the reference's Lua (5 k lines written for the real interpreter) parses."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present (GPU box)")
+    n = 0
+    for dirpath, _, files in os.walk(REF):
+        for f in files:
+            if f.endswith(".lua"):
+                lua_check.check_file(os.path.join(dirpath, f))
+                n += 1
+    assert n >= 40
+
+
+@pytest.mark.parametrize("src, msg", [
+    ("local function f(a)\n  if a then return 1\nend\n", "'end'"),                       # unclosed function
+    ("local t = {1, 2\nlocal u = 3\n", "'}'"),                                           # unclosed table
+    ("local function f() return ... end\n", "vararg"),                                    # ... outside a vararg function
+    ("break\n", "break"),                                                                 # break outside a loop
+    ("local x = = 3\n", "unexpected"),                                                    # garbage expression
+    ("f() = 3\n", "assign"),                                                              # call as assignment target
+    ("return 1\nlocal x = 2\n", "last statement"),                                       # code after return
+    ("x = 3 +\n", "unexpected"),                                                          # dangling operator
+    ("local s = 'abc\n", "unexpected character"),                                         # unfinished string
+])
+def test_checker_rejects_broken_lua(src, msg):
+    with pytest.raises(lua_check.LuaSyntaxError) as e:
+        lua_check.check_text(src, "t.lua")
+    assert msg in str(e.value)
+
+
+def test_checker_scope_rules():
+    rep = lua_check.check_text("""
+local a = 1
+local function f(x, ...) local n = select('#', ...); return x + a + n + undefined_name end
+for i = 1, 3 do local b = i end
+repeat local c = 1 until c == 1
+function M.g(self) return self end
+function obj:h() return self, misspelt end
+leak = b
+""", "t.lua")
+    assert set(rep.global_reads) == {"select", "undefined_name", "M", "obj", "misspelt", "b"}   # b is out of scope after the loop
+    assert set(lua_check.unknown_globals(rep)) == {"undefined_name", "M", "obj", "misspelt", "b"}
+    assert set(rep.global_writes) == {"leak"}
+    assert ("obj:h", 7) in rep.functions and ("M.g", 6) in rep.functions
