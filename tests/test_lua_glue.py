@@ -200,3 +200,60 @@ leak = b
     assert set(lua_check.unknown_globals(rep)) == {"undefined_name", "M", "obj", "misspelt", "b"}
     assert set(rep.global_writes) == {"leak"}
     assert ("obj:h", 7) in rep.functions and ("M.g", 6) in rep.functions
+
+
+def test_ffi_call_arity_matches_the_header():
+    """Every C call of the glue passes exactly as many arguments as include/bot7_b200.h declares (LuaJIT raises
+    'wrong number of arguments for function call' otherwise -- at run time, which nothing here can reach)."""
+    header = open(os.path.join(ROOT, "include", "bot7_b200.h")).read()
+    header = re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", header, flags=re.S))
+    protos = {}
+    for m in re.finditer(r"\b(b7_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(protos) >= 50
+    checked = 0
+    for f in GLUE_FILES:
+        rep = lua_check.check_file(os.path.join(LUA, f))
+        for path, line, n_args in rep.field_calls:
+            m = re.search(r"(?:^|\.)(b7_[a-z0-9_]+)$", path)
+            if not m:
+                continue
+            assert m.group(1) in protos, f"{f}:{line}: {m.group(1)} is not declared in the header"
+            assert n_args == protos[m.group(1)], f"{f}:{line}: {m.group(1)} called with {n_args} arguments, the header declares {protos[m.group(1)]}"
+            checked += 1
+    assert checked >= 20
+
+
+# Torch7 tensor / storage methods (torch7/doc/tensor.md, maths.md), nn.Module methods and Lua string methods the glue may call
+TORCH7_METHODS = {
+    "add", "addmm", "addmv", "abs", "apply", "byte", "cdiv", "clone", "cmul", "contiguous", "copy", "csub", "cumsum", "data", "dim",
+    "div", "dot", "double", "eq", "exp", "expand", "expandAs", "fill", "float", "ge", "gt", "index", "indexCopy", "int", "isContiguous",
+    "isSameSizeAs", "le", "log", "long", "lt", "max", "mean", "min", "mm", "mul", "mv", "nDimension", "nElement", "narrow", "ne", "neg",
+    "norm", "numel", "pow", "prod", "repeatTensor", "reshape", "resize", "resizeAs", "select", "set", "size", "sort", "sqrt", "squeeze",
+    "std", "storage", "stride", "sub", "sum", "t", "transpose", "type", "typeAs", "unfold", "var", "view", "viewAs", "zero",
+    "forward", "evaluate", "training", "get", "parameters", "getParameters", "updateOutput",
+    "find", "format", "gmatch", "gsub", "len", "lower", "match", "rep", "sub", "upper",
+}
+
+
+def test_every_method_called_by_the_glue_exists_somewhere():
+    """obj:method(...) with a misspelt method name is a run-time 'attempt to call method (a nil value)': every method name the
+    glue calls is a Torch7 tensor / nn / string method, a method one of the glue classes defines, or one the reference defines."""
+    defined = set()
+    for f in GLUE_FILES:
+        rep = lua_check.check_file(os.path.join(LUA, f))
+        defined |= {re.split(r"[:.]", path)[-1] for path, _ in rep.functions}
+    ref_defined = {"init", "class", "cache", "predict", "fantasize", "sample_hypers", "parse_hypers", "eval", "nominate", "update",
+                   "report", "generate", "network", "train"}
+    if os.path.isdir(REF):
+        ref_defined = set()
+        for dirpath, _, files in os.walk(REF):
+            for fn in files:
+                if fn.endswith(".lua"):
+                    r = lua_check.check_file(os.path.join(dirpath, fn))
+                    ref_defined |= {re.split(r"[:.]", path)[-1] for path, _ in r.functions}
+    for f in GLUE_FILES:
+        rep = lua_check.check_file(os.path.join(LUA, f))
+        for obj, m, line in rep.method_calls:
+            assert m in TORCH7_METHODS or m in defined or m in ref_defined, f"{f}:{line}: {obj}:{m}() -- no such method anywhere"

@@ -111,7 +111,7 @@ class Report:
         self.global_reads = {}        # name -> first line
         self.global_writes = {}       # name -> first line
         self.method_calls = []        # (object expression text, method, line)   obj:method(...)
-        self.field_calls = []         # (dotted path, line)                       a.b.c(...)
+        self.field_calls = []         # (dotted path, line, number of argument expressions)   a.b.c(...)
         self.functions = []           # (dotted name incl. ':' for methods, line)
         self.locals_declared = 0
 
@@ -401,9 +401,10 @@ class Parser:
             elif self.check("(") or self.tok[0] == "string" or self.check("{"):
                 if bare and kind == "global":
                     self.rep.global_reads.setdefault(info, line)
+                call_line = self.tok[2]
+                n_args = self.callargs()
                 if path is not None:
-                    self.rep.field_calls.append((path, self.tok[2]))
-                self.callargs()
+                    self.rep.field_calls.append((path, call_line, n_args))
                 path = (path or "") + "()"
                 kind, bare = "call", False
             else:
@@ -413,16 +414,20 @@ class Parser:
         return kind, path
 
     def callargs(self):
+        """Returns the number of argument expressions (a trailing call or `...` may expand to more at run time)."""
         if self.tok[0] == "string":
             self.i += 1
-        elif self.check("{"):
+            return 1
+        if self.check("{"):
             self.table()
-        else:
-            line = self.tok[2]
-            self.expect("(", "function arguments")
-            if not self.check(")"):
-                self.explist()
-            self.expect(")", "')' (to close '(' at line %d)" % line)
+            return 1
+        line = self.tok[2]
+        n = 0
+        self.expect("(", "function arguments")
+        if not self.check(")"):
+            n = self.explist()
+        self.expect(")", "')' (to close '(' at line %d)" % line)
+        return n
 
     def table(self):
         line = self.tok[2]
