@@ -298,6 +298,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    # NCCL's own log lines (the version banner at NCCL_DEBUG=WARN / VERSION, INFO lines) go to stderr: stdout carries ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from bot7_b200 import _lib as L
     from bot7_b200 import models, parallel
     dist = None
