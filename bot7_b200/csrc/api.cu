@@ -2,6 +2,7 @@
 // See include/bot7_b200.h for the contract and the reference interface each entry replaces.
 #include <math.h>
 #include <stdarg.h>
+#include <cmath>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -541,7 +542,9 @@ static int gp_retry_draw(b7_gp* gp, int s, int first_info) {
   double eps = 1e-8;
   const double growth = 1.1;
   while (true) {
-    if (eps > max_eps || !(max_eps == max_eps)) {
+    // a non-finite norm (NaN / inf entries, e.g. sigma_f^2 = exp(2 * 800)) can never be repaired by jitter and `eps > inf` never
+    // becomes true: give up at once (the reference's loop would not terminate; declared deviation, oracle/SPEC.md)
+    if (eps > max_eps || !std::isfinite(max_eps)) {
       // chol(I): L = I, beta = r, logdet = 0
       identity_kernel<<<(unsigned)((fs + 255) / 256), 256, 0, ctx->stream>>>(gp->fac + s * fs, gp->Np);
       b7_count(ctx);

@@ -361,9 +361,9 @@ def chol_jitter(K, eps=1e-8, growth=1.1, max_eps=None):
     itr = 0
     while True:
         itr += 1
-        # `eps > max_eps` is the reference's give-up test; a NaN norm would loop forever there
+        # `eps > max_eps` is the reference's give-up test; a NaN or infinite norm would loop forever there
         # (documented deviation: treated as give-up, same as the CUDA path).
-        if eps > max_eps or max_eps != max_eps:
+        if eps > max_eps or not math.isfinite(max_eps):
             L, info = potrf_lower(np.eye(n))
             return L, float("inf"), itr
         eps = eps * growth

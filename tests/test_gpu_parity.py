@@ -1038,3 +1038,22 @@ def test_bot_save_and_resume_through_the_t7_result_file(ctx, oracle, tmp_path):
     x, y = again.run_trial()
     assert again.nTrials == 7 and again.observed.shape == (7, 2) and np.array_equal(again.observed[:6], bot.observed)
     assert not any(np.array_equal(x[0], o) for o in bot.observed)              # a fresh grid row, not a repeat
+
+
+def test_nonfinite_hyper_parameters_return_instead_of_hanging(ctx, oracle):
+    """sigma_f^2 = exp(1600) = inf makes every entry of K infinite: the jitter policy's give-up test `eps > ||K||_F` can never
+    fire (utils/math.lua:184), so the retry loop must treat a non-finite norm as give-up (oracle/SPEC.md).  The call returns at
+    once with jitter = inf / a non-finite likelihood, and the handle stays usable."""
+    import time
+    Xo, y, hyp, _ = make_problem(oracle, 150, 2, 2, 10, 1e-2)
+    bad = hyp.copy()
+    bad[1, 2] = 800.0
+    t0 = time.perf_counter()
+    f = models.GPFactors(Xo, y, bad, flags=L.FIT_LOGML_ONLY)
+    assert time.perf_counter() - t0 < 5.0
+    ref = oracle.gp_fit(Xo, y, hyp[0], 0)["logml"]
+    assert abs(f.logml[0] - ref) <= 1e-9 * abs(ref)                     # the healthy draw next to it is unaffected
+    assert f.info[1] != 0 or not np.isfinite(f.logml[1]) or np.isinf(f.jitter[1])
+    g = f.refit(hyp, L.FIT_LOGML_ONLY)                                  # and the handle still works
+    assert abs(g.logml[1] - oracle.gp_fit(Xo, y, hyp[1], 0)["logml"]) <= 1e-9 * abs(ref)
+    f.free()

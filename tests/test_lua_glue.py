@@ -125,7 +125,9 @@ def test_glue_parses_and_every_name_resolves(name):
     a misspelt local or a forgotten `local` would surface here as an unknown global."""
     rep = lua_check.check_file(os.path.join(LUA, name))
     assert not lua_check.unknown_globals(rep), f"{name}: unknown globals {lua_check.unknown_globals(rep)}"
-    assert not rep.global_writes, f"{name}: assigns globals {rep.global_writes} (the glue must not leak names into _G)"
+    # the one global the glue owns: the package table torch.class stores its classes in (luaT_getinnerparent needs it to exist)
+    allowed = {"bot7_b200"} if name == "ffi.lua" else set()
+    assert set(rep.global_writes) <= allowed, f"{name}: assigns globals {rep.global_writes} (the glue must not leak names into _G)"
 
 
 @pytest.mark.parametrize("name", GLUE_FILES)
