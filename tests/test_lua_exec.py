@@ -513,3 +513,44 @@ return out[1], out[2], out[3], out[4]
 """)
     ref = oracle.acquisition(Xo, y, hyp, Xc, 0, False, oracle.SCORE_EI)
     assert r[0] == ref["idx"] and r[2] == r[0] and r[3] == r[1] and r[1] != r[0]
+
+
+# ---------------------------------------------------------------------------------- the interpreter on the reference's own Lua (CPU)
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_interpreter_runs_the_reference_slice_sampler_unchanged():
+    """Validation of the interpreter and the tensor stand-in on code that was written for the real runtime: the reference's
+    samplers/abstract.lua, samplers/slice.lua and utils/tensor.lua are loaded from the read-only reference tree, unmodified, and
+    sample a correlated-scale Gaussian; the same call protocol (sampler(f, X0, opt, f_args) -> nSamples x dim tensor) is what
+    lua/bot7_b200/models_gp.lua:sample_hypers relies on and what the test fixture's stand-in sampler implements."""
+    out = io.StringIO()
+    I = Interpreter(stdout=out)
+    torch7.install(I, seed=3)
+    I.run("bot7 = {samplers = {}, utils = {}}")
+    utils_tensor = I.run_file(os.path.join(REF, "utils", "tensor.lua"))[0]
+    I.G.get("bot7").get("utils").set("tensor", utils_tensor)
+    I.G.get("package").get("loaded").set("bot7.utils", I.G.get("bot7").get("utils"))
+    I.run_file(os.path.join(REF, "samplers", "abstract.lua"))
+    I.run_file(os.path.join(REF, "samplers", "slice.lua"))
+    r = I.run(r"""
+local sampler = bot7.samplers.slice()
+local evals = 0
+local function logp(x, args) evals = evals + 1; return -0.5 * (x[1][1] ^ 2 / args.v1 + x[1][2] ^ 2 / args.v2) end
+local x = torch.zeros(1, 2)
+local out = torch.Tensor(400, 2)
+for i = 1, 400 do
+  x = sampler(logp, x, {nSamples = 1}, {v1 = 1.0, v2 = 4.0})
+  out[i]:copy(x[1])
+end
+local gibbs = sampler(logp, torch.zeros(1, 2), {nSamples = 3, gibbs = true}, {v1 = 1.0, v2 = 4.0})
+return out, evals, gibbs, torch.type(sampler)
+""")
+    xs, evals, gibbs = r[0].a, r[1], r[2].a
+    assert xs.shape == (400, 2) and np.isfinite(xs).all() and evals > 1200 and r[3] == "bot7.samplers.slice"
+    assert abs(xs[:, 0].mean()) < 0.35 and abs(xs[:, 1].mean()) < 0.7
+    assert 0.6 < xs[:, 0].var() < 1.6 and 2.4 < xs[:, 1].var() < 6.4          # N(0, diag(1, 4)); 400 correlated draws
+    assert gibbs.shape == (3, 2) and np.isfinite(gibbs).all()
+    assert "Error" not in out.getvalue()

@@ -69,6 +69,27 @@ class LongStorage:
         return "\n".join(" %d" % x for x in self.v) + "\n[torch.LongStorage of size %d]" % len(self.v)
 
 
+class TensorStorage:
+    """t:storage(): only copy(LongStorage | table) is needed (utils/tensor.lua:shape)."""
+    lua_type = "userdata"
+
+    def __init__(self, t):
+        self.t = t
+
+    def lua_index(self, key):
+        if key == "copy":
+            def cp(self_, src):
+                vals = src.v if isinstance(src, LongStorage) else (src.a.ravel() if isinstance(src, Tensor) else _table_to_nested(src))
+                self_.t.a.ravel()[...] = vals
+                return self_
+            return cp
+        if key == "size":
+            return lambda self_: int(self_.t.a.size)
+        if isinstance(key, (int, float)):
+            return self.t._elem(self.t.a.ravel()[_i(key) - 1])
+        return None
+
+
 class Tensor:
     lua_type = "userdata"
 
@@ -110,8 +131,13 @@ class Tensor:
                     if not (1 <= lo <= hi <= n):
                         raise LuaError("index out of bound in dimension %d: {%d,%d} of %d" % (d, lo, hi, n))
                     idx.append(slice(lo - 1, hi))
+            elif isinstance(r, Tensor):
+                idx.append(r.a.astype(np.int64).ravel() - 1)         # t[{idx}]: a copy of the selected entries (numpy fancy index)
             else:
                 k = _i(r)
+                n = self.a.shape[d - 1]
+                if not 1 <= k <= n:
+                    raise LuaError("index %d out of range in dimension %d (size %d)" % (k, d, n))
                 idx.append(k - 1)
         return tuple(idx)
 
@@ -122,8 +148,11 @@ class Tensor:
                 return None
             return f
         if isinstance(key, LuaTable):
-            return self._wrap(self.a[self._ranges(key)])
+            r = self.a[self._ranges(key)]
+            return self._elem(r) if np.ndim(r) == 0 else self._wrap(r)      # t[{i, j}] with all scalars is a number
         if isinstance(key, Tensor):
+            if key.ttype == "torch.ByteTensor":
+                return self._wrap(self.a[key.a.astype(bool)])
             raise LuaError("tensor-valued index is not supported by tools/minilua")
         k = _i(key)
         if self.a.ndim == 0:
@@ -301,12 +330,14 @@ class Tensor:
 
     def m_expand(self, *sz):
         shape = _sizes(sz)
-        if len(shape) != self.a.ndim:
-            raise LuaError("expand: the number of sizes must match the number of dimensions")
-        for s, t in zip(self.a.shape, shape):
+        # torch7 (THTensor_expand): at least as many sizes as dimensions; missing leading dimensions are prepended as singletons
+        if len(shape) < self.a.ndim:
+            raise LuaError("expand: the number of sizes provided must be greater or equal to the number of dimensions in the tensor")
+        src = self.a.reshape((1,) * (len(shape) - self.a.ndim) + self.a.shape)
+        for s, t in zip(src.shape, shape):
             if s != 1 and s != t:
                 raise LuaError("expand: only singleton dimensions can be expanded")
-        return self._wrap(np.broadcast_to(self.a, shape))
+        return self._wrap(np.broadcast_to(src, shape))
 
     def m_expandAs(self, o):
         return self.m_expand(*o.a.shape)
@@ -334,7 +365,23 @@ class Tensor:
             raise LuaError("in-place operation on an expanded tensor")
 
     def _other(self, x):
-        return x.a if isinstance(x, Tensor) else x
+        """The operand of an element-wise in-place operation: TH pairs elements in storage order when the sizes differ but the
+        number of elements agrees (numpy would broadcast (M, 1) against (M,) into (M, M))."""
+        if not isinstance(x, Tensor):
+            return x
+        if x.a.shape == self.a.shape:
+            return x.a
+        if x.a.size == self.a.size:
+            return x.a.reshape(self.a.shape)
+        raise LuaError("inconsistent tensor size: %s vs %s" % (list(self.a.shape), list(x.a.shape)))
+
+    def _take(self, src):
+        """x:op(src, ...): the result goes to x, resized like src."""
+        if src is not self:
+            if self.a.shape != src.a.shape:
+                self.a = np.empty(src.a.shape, dtype=self.a.dtype)
+            self.a[...] = src.a
+        return self
 
     def m_fill(self, v):
         self._writable()
@@ -350,20 +397,21 @@ class Tensor:
             raise LuaError("copy: tensor expected, got %s" % lua_type(o))
         if o.a.size != self.a.size:
             raise LuaError("copy: sizes do not match (%s vs %s)" % (self.a.shape, o.a.shape))
-        self.a[...] = o.a.reshape(self.a.shape) if o.a.shape != self.a.shape else o.a
+        self.a[...] = self._other(o)
         return self
 
     def m_add(self, *r):
         self._writable()
         if len(r) == 1:                                 # x:add(value) / x:add(tensor)
-            o = self._other(r[0])
-            self.a += o.reshape(self.a.shape) if isinstance(r[0], Tensor) and o.shape != self.a.shape else o
+            self.a += self._other(r[0])
         elif len(r) == 2 and not isinstance(r[0], Tensor):   # x:add(value, tensor)
-            self.a += r[0] * r[1].a
+            self.a += r[0] * self._other(r[1])
         elif len(r) == 2:                                # x:add(tensor1, tensor2 | value)
-            self.a[...] = r[0].a + self._other(r[1])
+            self._take(r[0])
+            self.a += self._other(r[1])
         elif len(r) == 3:                                # x:add(tensor1, value, tensor2)
-            self.a[...] = r[0].a + r[1] * r[2].a
+            self._take(r[0])
+            self.a += r[1] * self._other(r[2])
         else:
             raise LuaError("add: unsupported arguments")
         return self
@@ -373,51 +421,87 @@ class Tensor:
         if len(r) == 1:
             self.a -= self._other(r[0])
         else:
-            self.a -= r[0] * r[1].a
+            self.a -= r[0] * self._other(r[1])
         return self
 
-    def m_mul(self, v):
+    def m_mul(self, *r):
         self._writable()
-        if isinstance(v, Tensor):
+        if len(r) == 2:                                  # x:mul(src, value)
+            self._take(r[0])
+            r = r[1:]
+        if isinstance(r[0], Tensor):
             raise LuaError("mul: number expected (use cmul for tensors)")
-        self.a *= v
+        self.a *= r[0]
         return self
 
-    def m_div(self, v):
+    def m_div(self, *r):
         self._writable()
-        if isinstance(v, Tensor):
+        if len(r) == 2:
+            self._take(r[0])
+            r = r[1:]
+        if isinstance(r[0], Tensor):
             raise LuaError("div: number expected (use cdiv for tensors)")
         if self.a.dtype.kind == "f":
-            self.a /= v
+            self.a /= r[0]
         else:
-            self.a //= int(v)
+            self.a //= int(r[0])
         return self
 
     def m_cmul(self, *r):
         self._writable()
-        if len(r) == 1:
-            self.a *= r[0].a.reshape(self.a.shape) if r[0].a.shape != self.a.shape else r[0].a
-        else:
-            self.a[...] = r[0].a * r[1].a
+        if len(r) == 2:
+            self._take(r[0])
+            r = r[1:]
+        self.a *= self._other(r[0])
         return self
 
     def m_cdiv(self, *r):
         self._writable()
-        if len(r) == 1:
-            self.a /= r[0].a
-        else:
-            self.a[...] = r[0].a / r[1].a
+        if len(r) == 2:
+            self._take(r[0])
+            r = r[1:]
+        with np.errstate(all="ignore"):
+            self.a /= self._other(r[0])
         return self
 
-    def m_pow(self, v):
+    def m_cpow(self, *r):
         self._writable()
+        if len(r) == 2:
+            self._take(r[0])
+            r = r[1:]
         with np.errstate(all="ignore"):
-            self.a[...] = self.a ** v
+            self.a[...] = self.a ** self._other(r[0])
+        return self
+
+    def m_mv(self, m, v):
+        self._writable()
+        self.a[...] = m.a @ v.a
+        return self
+
+    def m_storage(self):
+        return TensorStorage(self)
+
+    def m_pow(self, *r):
+        self._writable()
+        if len(r) == 2:                                  # x:pow(src, value)
+            self._take(r[0])
+            r = r[1:]
+        with np.errstate(all="ignore"):
+            self.a[...] = self.a ** r[0]
+        return self
+
+    def m_clamp(self, lo, hi):
+        self._writable()
+        # TH_TENSOR_APPLY: (x < lo) ? lo : ((x > hi) ? hi : x) -- comparison based, a NaN passes through
+        x = self.a
+        self.a[...] = np.where(x < lo, lo, np.where(x > hi, hi, x))
         return self
 
     def _unary(f):
-        def m(self):
+        def m(self, src=None):
             self._writable()
+            if src is not None:
+                self._take(src)
             with np.errstate(all="ignore"):
                 self.a[...] = f(self.a)
             return self
@@ -425,6 +509,7 @@ class Tensor:
 
     m_sqrt, m_exp, m_log, m_abs, m_neg, m_floor, m_ceil = (_unary(np.sqrt), _unary(np.exp), _unary(np.log), _unary(np.abs), _unary(np.negative),
                                                           _unary(np.floor), _unary(np.ceil))
+    m_cos, m_sin, m_tan, m_tanh, m_round = _unary(np.cos), _unary(np.sin), _unary(np.tan), _unary(np.tanh), _unary(np.round)
     del _unary
 
     def m_apply(self, f):
@@ -483,12 +568,56 @@ class Tensor:
         return float(np.dot(self.a.ravel(), o.a.ravel()))
 
     def _cmp(f):
-        def m(self, o):
-            return Tensor(f(self.a, o.a if isinstance(o, Tensor) else o).astype(np.uint8), "torch.ByteTensor")
+        def m(self, *r):
+            if len(r) == 2:                              # x:ge(src, value): 0 / 1 into x, keeping x's type
+                src, o = r
+                res = f(src.a, o.a if isinstance(o, Tensor) else o)
+                if self.a.shape != src.a.shape:
+                    self.a = np.empty(src.a.shape, dtype=self.a.dtype)
+                self.a[...] = res
+                return self
+            o = r[0]
+            return Tensor(f(self.a, self._other(o) if isinstance(o, Tensor) else o).astype(np.uint8), "torch.ByteTensor")
         return m
 
     m_eq, m_ne, m_lt, m_le, m_gt, m_ge = _cmp(np.equal), _cmp(np.not_equal), _cmp(np.less), _cmp(np.less_equal), _cmp(np.greater), _cmp(np.greater_equal)
     del _cmp
+
+    def m_maskedFill(self, mask, val):
+        self._writable()
+        self.a[mask.a.astype(bool).reshape(self.a.shape)] = val
+        return self
+
+    def m_maskedSelect(self, mask):
+        return self._wrap(np.ascontiguousarray(self.a[mask.a.astype(bool).reshape(self.a.shape)]))
+
+    def m_any(self):
+        return bool(np.any(self.a != 0))
+
+    def m_all(self):
+        return bool(np.all(self.a != 0))
+
+    def m_nonzero(self):
+        idx = np.argwhere(self.a != 0).astype(np.int64) + 1
+        if idx.shape[0] == 0:
+            return Tensor(np.zeros((0,), dtype=np.int64), "torch.LongTensor")       # dim() == 0, as torch7's empty result
+        return Tensor(np.ascontiguousarray(idx), "torch.LongTensor")
+
+    def m_indexCopy(self, dim, idx, src):
+        self._writable()
+        ax = _i(dim) - 1
+        k = idx.a.astype(np.int64).ravel() - 1
+        sl = [slice(None)] * self.a.ndim
+        sl[ax] = k
+        self.a[tuple(sl)] = src.a
+        return self
+
+    def m_indexFill(self, dim, idx, val):
+        self._writable()
+        sl = [slice(None)] * self.a.ndim
+        sl[_i(dim) - 1] = idx.a.astype(np.int64).ravel() - 1
+        self.a[tuple(sl)] = val
+        return self
 
     def m_totable(self):
         def conv(a):
@@ -510,7 +639,7 @@ def make_tensor(ttype, args, rng=None):
         return Tensor(args[0].a if args[0].ttype == ttype else args[0].a.astype(dt), ttype)     # shares the storage
     # torch.Tensor(sizes...) is uninitialised memory: poison it, so that a glue that reads before it writes is caught
     a = np.empty(_sizes(args), dtype=dt)
-    a[...] = np.nan if dt in (np.float64, np.float32) else -(2 ** 30)
+    a[...] = np.nan if dt in (np.float64, np.float32) else (-(2 ** 30) if dt in (np.int64, np.int32) else 171)
     return Tensor(a, ttype)
 
 
@@ -619,7 +748,7 @@ def install(I, seed=0):
     def fresh(f):
         """torch.f(tensor, ...) -> new tensor (the method works in place on a clone); torch.f(result, tensor, ...) fills result."""
         def g(*a):
-            if len(a) >= 2 and isinstance(a[0], Tensor) and isinstance(a[1], Tensor) and f in ("sqrt", "exp", "log", "abs", "neg", "pow", "mul", "div"):
+            if len(a) >= 2 and isinstance(a[0], Tensor) and isinstance(a[1], Tensor) and f in ("sqrt", "exp", "log", "abs", "neg", "pow", "mul", "div", "cos", "sin", "tanh", "floor", "ceil"):
                 res, src, rest = a[0], a[1], a[2:]
                 res.m_resizeAs(src).m_copy(src)
                 getattr(Tensor, "m_" + f)(res, *rest)
@@ -633,8 +762,12 @@ def install(I, seed=0):
             return a[0].m_clone().m_add(*a[1:])
         return a[1].m_clone().m_add(a[0])
 
-    def t_range(lo, hi, step=1):
-        return Tensor(np.arange(lo, hi + (1e-9 if step > 0 else -1e-9), step, dtype=np.float64), "torch.DoubleTensor")
+    def t_range(lo, hi, step=1, ttype=None):
+        if isinstance(step, str):                       # torch.range(a, b, 'torch.LongTensor')
+            step, ttype = 1, step
+        tt = ttype or "torch.DoubleTensor"
+        n = int(np.floor((hi - lo) / step + 1e-12)) + 1
+        return Tensor((lo + step * np.arange(max(n, 0))).astype(TYPES[tt]), tt)
 
     def t_mm(a, b):
         return Tensor(np.ascontiguousarray(a.a @ b.a), a.ttype)
@@ -648,7 +781,9 @@ def install(I, seed=0):
                     ("manualSeed", t_seed), ("cat", t_cat), ("add", t_add), ("range", t_range), ("mm", t_mm),
                     ("cmul", lambda a, b: a.m_clone().m_cmul(b)), ("cdiv", lambda a, b: a.m_clone().m_cdiv(b)),
                     ("mul", fresh("mul")), ("div", fresh("div")), ("sqrt", fresh("sqrt")), ("exp", fresh("exp")), ("log", fresh("log")),
-                    ("abs", fresh("abs")), ("pow", fresh("pow")), ("neg", fresh("neg")),
+                    ("abs", fresh("abs")), ("pow", fresh("pow")), ("neg", fresh("neg")), ("floor", fresh("floor")), ("ceil", fresh("ceil")),
+                    ("cos", fresh("cos")), ("sin", fresh("sin")), ("tanh", fresh("tanh")),
+                    ("mv", lambda m, v: Tensor(np.ascontiguousarray(m.a @ v.a), m.ttype)),
                     ("min", lambda t, d=None: t.m_min(d)), ("max", lambda t, d=None: t.m_max(d)), ("sum", lambda t, d=None: t.m_sum(d)),
                     ("mean", lambda t, d=None: t.m_mean(d)), ("dot", lambda a, b: a.m_dot(b)), ("norm", lambda t, p=2: t.m_norm(p)),
                     ("eye", lambda n: Tensor(np.eye(_i(n)), "torch.DoubleTensor")),
