@@ -10,8 +10,8 @@ which replaces, in the global `bot7` table (reference init.lua:28-40),
     bot7.models.dngo          -> models_dngo.lua   (basis + BLR head on the GPU: b7_mlp_features, b7_blr_*, b7_dngo_score)
     bot7.bots.bayesopt        -> bayesopt.lua      (eval+nominate = one batched device call; config.bot.nGPU > 1 -> b7_comm_*)
 Everything else in bot7 (config tables, trial loop, objectives, nnTools) is untouched.
-No Lua runtime exists in the build image; this glue is exercised through its Python twin
-(bot7_b200/*.py), which calls the same C symbols with the same arguments.
+No Lua runtime exists in the build image: this glue is executed by tests/test_lua_exec.py under the interpreter of
+tools/minilua (Torch7 / LuaJIT-FFI stand-ins over the real library) and mirrored by its Python twin (bot7_b200/*.py).
 --]]
 local M = {}
 M.ffi      = require('bot7_b200.ffi')

@@ -7,7 +7,12 @@ Two kinds of content, labelled on every function:
 
 * PINNED  -- op-for-op restatement of arithmetic that is visible in the reference tree
   (/root/reference, cited file:line).  Checked against the known answers of SURVEY.md section 4
-  in tests/test_oracle_golden.py.
+  in tests/test_oracle_golden.py AND (round 2) against outputs of the reference source itself:
+  tests/golden/make_ref_exec.py executes the reference's own Lua files, unmodified, under the Lua
+  interpreter of tools/minilua and stores the results in tests/golden/ref_exec.npz;
+  tests/test_ref_exec.py asserts that the functions below reproduce them bit for bit (Sobol in eight
+  configurations, direction numbers, XOR, erf / cdf / pdf, EI incl. its NaN policy, the confidence
+  bound, the jitter policy's iterations and factor, steal / remove, the three objectives).
 * DECLARED -- the GP / Bayesian-linear-regression arithmetic lives in the un-vendored, un-versioned
   luarocks dependency "gp" (gpTorch7, bot7-scm-1.rockspec:18, models/init.lua:15).  Its source is
   not available, the reference ships no tests or golden vectors for it, and no Lua runtime exists
