@@ -143,6 +143,49 @@ def generate():
                       ("lcb_pos", "{tradeoff = 0.5, bound = 'lower', sign = 1.0}")]:
         G["score_" + name] = I.run("return bot7.scores.confidence_bound.compute(MEAN, VAR, %s)" % cfg)[0].a.copy().reshape(-1)
 
+    # ---- bots/bayesopt.lua eval + nominate (:56-99): priming draw, S draws, sequential sum, one divide, score:max(1) -------
+    # The real bot class and the real EI / bound objects run; the model is a stand-in whose predict returns prescribed moments
+    # per draw (the GP itself lives in the absent gp rock), and the parent class bots/abstract.lua is replaced by a stub that
+    # only carries the fields eval / nominate read.
+    S, Mb = 5, 300
+    means, vars_ = rng.standard_normal((S, Mb)) * 0.5, np.abs(rng.standard_normal((S, Mb))) * 0.2 + 1e-3
+    means[:, 17] = means[:, 4]                          # two candidates with identical moments in every draw: a tie for the argmax
+    vars_[:, 17] = vars_[:, 4]
+    means[:, 4] -= 3.0                                  # ... made the best ones
+    means[:, 17] -= 3.0
+    yobs = rng.standard_normal((40, 1))
+    G["bo_means"], G["bo_vars"], G["bo_yobs"] = means, vars_, yobs
+    I.G.set("MEANS", tensor(means))
+    I.G.set("VARS", tensor(vars_))
+    I.G.set("YOBS", tensor(yobs))
+    loaded = I.G.get("package").get("loaded")
+    loaded.set("bot7.models", LuaTable())
+    loaded.set("bot7.scores", I.G.get("bot7").get("scores"))
+    I.run("bot7.bots = {}; local a = torch.class('bot7.bots.abstract'); function a:__init() end; function a:configure(c) return c or {} end")
+    I.run_file(os.path.join(REF, "bots", "bayesopt.lua"))
+    BO = r"""
+local S = MEANS:size(1)
+local order = {}
+local fake = {k = 0}
+function fake:class() return 'gp.models.gp_regressor' end
+function fake:sample_hypers(X, Y, a, b, single) self.k = self.k + 1; local s = (self.k - 1) % S + 1; order[#order + 1] = s; return torch.Tensor{{s}} end
+function fake:parse_hypers(h) return h end
+function fake:predict(X0, Y0, X1, hyp, req) local s = hyp[1][1]; return {mean = MEANS[s]:clone():view(-1, 1), var = VARS[s]:clone():view(-1, 1)} end
+local bot = bot7.bots.bayesopt(nil, nil, {bot = {nSamples = S, nInitial = 0}}, {model = fake, score = SCORE})
+bot.observed, bot.responses, bot.candidates, bot.nTrials = torch.zeros(YOBS:size(1), 2), YOBS, torch.zeros(MEANS:size(2), 2), 3
+local score = bot:eval()
+fake.k = 0
+local idx = bot:nominate()
+return score, idx, torch.Tensor(order)
+"""
+    for name, ctor, trade in [("ei", "bot7.scores.expected_improvement{tradeoff = 0.0}", 0.0),
+                              ("ucb", "bot7.scores.confidence_bound{tradeoff = 2.0, bound = 'upper', sign = 1.0}", None)]:
+        I.G.set("config", LuaTable({"tradeoff": trade}) if trade is not None else None)     # EI.compute's global (see above)
+        I.G.set("SCORE", I.run("return " + ctor)[0])
+        r = I.run(BO, "=bayesopt " + name)
+        G["bo_%s_score" % name], G["bo_%s_idx" % name], G["bo_%s_order" % name] = r[0].a.copy(), r[1].a.copy(), r[2].a.copy()
+    I.G.set("config", None)
+
     # ---- utils.math.chol: plain success, jitter success, give-up ---------------------------------------------------------
     A = rng.standard_normal((6, 6))
     spd = A @ A.T + 6 * np.eye(6)
@@ -196,6 +239,8 @@ if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference tree not present: nothing to execute")
     G, printed = generate()
+    if os.environ.get("REF_EXEC_FAST"):
+        OUT = "/tmp/ref_exec_fast.npz"                   # the debugging subset never replaces the committed file
     np.savez_compressed(OUT, **G)
     print("wrote %s: %d arrays, %d bytes" % (OUT, len(G), os.path.getsize(OUT)))
     for k in sorted(G):

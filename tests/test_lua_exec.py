@@ -550,6 +550,27 @@ return out, evals, gibbs, torch.type(sampler)
 """)
     xs, evals, gibbs = r[0].a, r[1], r[2].a
     assert xs.shape == (400, 2) and np.isfinite(xs).all() and evals > 1200 and r[3] == "bot7.samplers.slice"
+    # The Python twin (bot7_b200/samplers.py) restates this control flow and draws its random numbers in the same order: fed
+    # by the same generator it must walk the SAME chain -- which pins the twin (and with it the speculative
+    # sampler that the GPU tests compare with it) to the executed reference.
+    sys.path.insert(0, ROOT)
+    from bot7_b200 import samplers
+    rng = np.random.default_rng(3)
+    count = [0]
+
+    def logp(x, args):
+        count[0] += 1
+        return -0.5 * (x[0, 0] ** 2 / args["v1"] + x[0, 1] ** 2 / args["v2"])
+    tw = samplers.slice()
+    x = np.zeros((1, 2))
+    chain = np.empty((400, 2))
+    for i in range(400):
+        x = tw(logp, x, {"nSamples": 1}, {"v1": 1.0, "v2": 4.0}, rng)
+        chain[i] = x[0]
+    g2 = tw(logp, np.zeros((1, 2)), {"nSamples": 3, "gibbs": True}, {"v1": 1.0, "v2": 4.0}, rng)
+    # same number of density evaluations = every accept / reject / step-out decision coincided; the values differ by rounding only
+    # (the direction's norm: BLAS dot in numpy vs a sum of squares), the Gibbs draws (no norm) not at all
+    assert count[0] == evals and np.allclose(chain, xs, rtol=0.0, atol=1e-12) and np.array_equal(g2, gibbs)
     assert abs(xs[:, 0].mean()) < 0.35 and abs(xs[:, 1].mean()) < 0.7
     assert 0.6 < xs[:, 0].var() < 1.6 and 2.4 < xs[:, 1].var() < 6.4          # N(0, diag(1, 4)); 400 correlated draws
     assert gibbs.shape == (3, 2) and np.isfinite(gibbs).all()

@@ -105,6 +105,31 @@ def test_compaction_and_objectives_equal_the_executed_reference(oracle, G):
         assert np.max(np.abs(ref - y) / np.maximum(np.abs(y), 1.0)) <= 4e-16
 
 
+def _draw_scores(oracle, G, kind):
+    m, v, fmin = G["bo_means"], G["bo_vars"], float(G["bo_yobs"].min())
+    order = G["bo_%s_order" % kind].astype(int)
+    S = m.shape[0]
+    # eval: one priming draw (result unused, bots/bayesopt.lua:68), then S draws; nominate calls eval again
+    assert order.shape == (2 * (S + 1),) and np.array_equal(order[:S + 1], order[S + 1:])
+    used = order[1:S + 1] - 1
+    if kind == "ei":
+        return np.array([oracle.ei_compute(m[s], v[s], fmin, 0.0) for s in used]), used
+    return np.array([oracle.cb_compute(m[s], v[s], 2.0, "upper", 1.0) for s in used]), used
+
+
+@pytest.mark.parametrize("kind", ["ei", "ucb"])
+def test_oracle_draw_average_and_argmax_equal_the_executed_bayesopt(oracle, G, kind):
+    """bots/bayesopt.lua:56-99 executed with the reference's own score objects: sequential sum from zero in draw order, one
+    divide, first maximum (candidates 5 and 18 tie by construction in the EI case)."""
+    per_draw, _ = _draw_scores(oracle, G, kind)
+    score = oracle.mc_average(per_draw)
+    assert np.array_equal(score, G["bo_%s_score" % kind])
+    best, idx, nans = oracle.argmax_first(score)
+    assert idx == int(G["bo_%s_idx" % kind][0]) and nans == 0
+    if kind == "ei":
+        assert idx == 5 and score[4] == score[17]
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
 def test_committed_vectors_are_what_the_reference_produces_here():
     """Re-executes a subset of the generator live (one Sobol case; all of math / scores / chol / steal / objectives) and compares it
@@ -161,3 +186,27 @@ def test_cuda_grid_compaction_equals_the_executed_reference(ctx, G):
     rest = np.array([g.read(g.original_index(c) - 1, 1)[0] for c in range(1, g.size() + 1)])
     assert np.array_equal(rest, G["steal_rest"])
     g.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["ei", "ucb"])
+def test_cuda_draw_average_and_argmax_equal_the_executed_bayesopt(ctx, oracle, G, kind):
+    """The fused scoring pass (per-draw EI / bound, sequential average, first-max argmax) on the moments the executed
+    bots/bayesopt.lua saw, in the draw order it used."""
+    import ctypes as C
+    from bot7_b200 import _lib as L
+    _, used = _draw_scores(oracle, G, kind)
+    mean = np.ascontiguousarray(G["bo_means"][used])
+    var = np.ascontiguousarray(G["bo_vars"][used])
+    S, M = mean.shape
+    out = np.empty(M)
+    am, best, nn = C.c_int64(), C.c_double(), C.c_int64()
+    k, trade, bound, sign = (L.SCORE_EI, 0.0, 0, -1.0) if kind == "ei" else (L.SCORE_CB, 2.0, 1, 1.0)
+    L.check(L.lib().b7_score_moments(ctx.handle, k, L.dptr(mean), L.dptr(var), S, M, trade, bound, sign, float(G["bo_yobs"].min()),
+                                     L.dptr(out), C.byref(am), C.byref(best), C.byref(nn)), "b7_score_moments")
+    ref = G["bo_%s_score" % kind]
+    assert am.value == int(G["bo_%s_idx" % kind][0]) and nn.value == 0              # selected index: bit-exact requirement
+    if kind == "ucb":
+        assert np.array_equal(out, ref)                                              # sqrt / mul / add only
+    else:
+        assert float(np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-300))) <= 1e-7

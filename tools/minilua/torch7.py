@@ -562,6 +562,8 @@ class Tensor:
         return float(np.var(self.a, ddof=1))
 
     def m_norm(self, p=2):
+        if p == 2:
+            return float(np.sqrt(np.sum(self.a * self.a)))           # TH: sqrt of the sum of squares
         return float(np.sum(np.abs(self.a) ** p) ** (1.0 / p))
 
     def m_dot(self, o):
