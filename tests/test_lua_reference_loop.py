@@ -1,0 +1,175 @@
+"""The reference's OWN control plane driving the LuaJIT glue: init.lua, hyperparam.lua, bots/abstract.lua, bots/bayesopt.lua,
+samplers/slice.lua, grids/abstract.lua, scores/abstract.lua, utils/*.lua, benchmarks/*.lua and examples/run_benchmark.lua are
+loaded UNMODIFIED from the read-only reference tree under tools/minilua, `require('bot7_b200').install()` swaps in the glue
+classes, and whole Bayesian-optimisation experiments run -- BASELINE.json's config 1 (examples/run_benchmark.lua: Branin-Hoo,
+bayesopt EI, GP ARD-SE, Sobol candidates) through the reference's own example script.
+
+This can only run where the reference tree is (the build container), which has no GPU; the library has no CPU path.  So the
+glue's `ffi.load` is answered by tests/fake_b7_lib.py, an oracle-backed object with the C ABI's signatures.  What is under test
+is therefore the PROTOCOL between the reference's classes, the glue and the C ABI -- constructor chains, which object owns which
+field, compacted vs original numbering across `utils.tensor.steal` and `b7_grid_remove`, handle lifetimes -- in the one setting
+where the real reference classes are the callers.  (The glue against the REAL library is tests/test_lua_exec.py on the GPU.)
+Absent dependencies are stubbed and named: penlight's tablex (deepcopy / find), the `gp` rock (an empty `gp.models` table, which is
+exactly what install() fills), nnTools (DNGO's trainer: not on this path), torch.CmdLine.
+"""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from minilua import Interpreter, LuaError  # noqa: E402,F401
+from minilua import ffi as ffi_mod  # noqa: E402
+from minilua import torch7  # noqa: E402
+from minilua.harness import LUA_DIR  # noqa: E402
+from minilua.interp import LuaTable  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+
+CMDLINE = r"""
+local Cmd = torch.class('torch.CmdLine')
+function Cmd:__init() self.opts = {} end
+function Cmd:text() end
+function Cmd:option(name, default, help) self.opts[#self.opts + 1] = {name = name:gsub('^%-+', ''), default = default} end
+function Cmd:parse(arg)
+  local o = {}
+  for _, op in ipairs(self.opts) do o[op.name] = op.default end
+  local i = 1
+  while i <= #arg do
+    local key = arg[i]:gsub('^%-+', '')
+    local def = o[key]
+    assert(def ~= nil, 'unknown option ' .. arg[i])
+    local v = arg[i + 1]
+    if type(def) == 'number' then v = tonumber(v) elseif type(def) == 'boolean' then v = (v == 'true') end
+    o[key] = v
+    i = i + 2
+  end
+  return o
+end
+"""
+
+
+class Runtime:
+    def __init__(self, oracle, seed=7):
+        from fake_b7_lib import FakeB7
+        self.out = io.StringIO()
+        self.I = I = Interpreter(search_path=[("bot7", REF), ("bot7_b200", LUA_DIR)], stdout=self.out)
+        torch7.install(I, seed)
+        loaded = I.G.get("package").get("loaded")
+
+        def deepcopy(t):                                   # penlight tablex.deepcopy: tables recursively, metatables kept
+            if isinstance(t, LuaTable):
+                n = LuaTable()
+                n.meta = t.meta
+                for k, v in t.hash.items():
+                    n.hash[k] = deepcopy(v)
+                return n
+            return t
+
+        def find(t, v, start=1):
+            for k in range(int(start), t.length() + 1):
+                if I.eq(t.get(k), v):
+                    return k
+            return [None]
+        tablex = LuaTable()
+        tablex.set("deepcopy", deepcopy)
+        tablex.set("find", find)
+        loaded.set("pl.tablex", tablex)
+        loaded.set("gp.models", LuaTable())                 # the absent rock: an empty module table
+        for n in ("builder", "trainer", "evaluator", "buffers"):
+            loaded.set("bot7.nnTools." + n, LuaTable())
+        for n in ("optim", "xlua"):
+            loaded.set(n, LuaTable())
+        loaded.set("nn", I.G.get("nn"))
+        I.run(CMDLINE, "=torch.CmdLine")
+        self.fake = FakeB7(oracle)
+        self.ffi = ffi_mod.Runtime(I, lambda name: self.fake)
+        self.ffi.install()
+        I.run("require 'bot7'; require('bot7_b200').install()", "=setup")
+
+    def close(self):
+        self.ffi.close()
+
+
+@pytest.fixture()
+def rt(oracle):
+    r = Runtime(oracle)
+    yield r
+    r.close()
+
+
+def test_reference_example_script_runs_config_1_through_the_glue(rt, oracle):
+    """examples/run_benchmark.lua, unmodified, with its own command line: Branin-Hoo, bayesopt + EI, noiseless GP, Sobol grid."""
+    I, fake = rt.I, rt.fake
+    args = LuaTable({k + 1: v for k, v in enumerate(["-budget", "9", "-grid_size", "300", "-nInitial", "3", "-verbose", "1", "-benchmark", "braninhoo"])})
+    I.G.set("arg", args)
+    I.run_file(os.path.join(REF, "examples", "run_benchmark.lua"))
+    text = rt.out.getvalue()
+    assert "Trial: 9 of 9" in text and "Best response" in text and "Error" not in text
+    calls = fake.calls
+    # one Sobol grid by the glue's generator (host tensor, as the reference's Grids[...](config)() returns it) + its device copy
+    assert calls.count("b7_sobol_generate") == 1 and calls.count("b7_grid_from_host") == 1
+    assert calls.count("b7_grid_remove") == 9                           # every nomination leaves the device grid too
+    assert calls.count("b7_acq_score") == 6                             # trials 4 .. 9 (nTrials <= nInitial picks at random)
+    assert calls.count("b7_gp_refit") > 50                              # the reference's slice sampler evaluating the glue's density
+    # everything that was created has been released once the bot is gone, the context last
+    import gc
+    del I
+    rt.I.G.set("bot", None)
+    gc.collect()
+    rt.close()
+    kinds = [f[0] for f in fake.freed]
+    assert kinds[-1] == "ctx" and fake.freed[-1][2] == 0, fake.freed[-3:]
+    assert kinds.count("grid") == 1 and kinds.count("gp") >= 6
+
+
+def test_reference_bot_and_glue_stay_consistent_trial_by_trial(rt, oracle):
+    """The same experiment driven trial by trial: after every run_trial the host candidates (compacted by the reference's
+    utils.tensor.steal) and the device grid (compacted by b7_grid_remove) hold the same rows in the same order, the nominee is
+    the row the acquisition selected, and the model's chain state follows bots/abstract.lua:148 / bots/bayesopt.lua:68-75."""
+    I, fake = rt.I, rt.fake
+    seen = []
+
+    def check(bot):
+        cand = I.index(bot, "candidates").a
+        grids = [o for o in fake.handles.values() if o["kind"] == "grid"]
+        assert len(grids) == 1
+        dev = grids[0]["X"][grids[0]["live"]]
+        assert np.array_equal(cand, dev)
+        obs, resp = I.index(bot, "observed"), I.index(bot, "responses")
+        seen.append((None if obs is None else obs.a.copy(), None if resp is None else resp.a.copy(), int(I.index(bot, "nTrials"))))
+        return True
+    I.G.set("CHECK", check)
+    r = I.run(r"""
+local benchmarks = require('bot7.benchmarks')
+local hypers = {bot7.hyperparam('x1', 0, 1), bot7.hyperparam('x2', 0, 1)}
+local expt = {xDim = 2, yDim = 1,
+              bot = {type = 'bo', nInitial = 2, budget = 7, nSamples = 3, verbose = 0},
+              model = {noiseless = true, nSamples = 2},
+              grid = {type = 'sobol', size = 200},
+              score = {type = 'confidence_bound', tradeoff = 1.5}}
+local bot = bot7.bots.bayesopt(benchmarks.braninhoo, hypers, expt)
+assert(torch.type(bot) == 'bot7_b200.bots.bayesopt' and torch.type(bot.model) == 'bot7_b200.models.gp_regressor')
+assert(torch.type(bot.score) == 'bot7_b200.scores.confidence_bound' and bot.score.config.tradeoff == 1.5)
+CHECK(bot)
+for t = 1, 7 do
+  bot:run_trial()
+  CHECK(bot)
+end
+return bot.observed, bot.responses, bot.model.hyp, bot.candidates:size(1)
+""", "=trial loop")
+    obs, resp, hyp, n_left = r[0].a, r[1].a, r[2].a, r[3]
+    assert obs.shape == (7, 2) and resp.shape == (7, 1) and n_left == 193
+    assert np.allclose(resp[:, 0], oracle.braninhoo(obs), rtol=1e-14, atol=0.0)
+    assert hyp.shape == (1, 5) and np.isfinite(hyp).all()
+    # all observed points are distinct rows of the original Sobol grid, i.e. nothing was nominated twice
+    grid = oracle.sobol_points(2, 200)
+    rows = [int(np.flatnonzero((grid == x).all(1))[0]) for x in obs]
+    assert len(set(rows)) == 7
+    assert [s[2] for s in seen] == list(range(0, 8))
+    assert fake.calls.count("b7_acq_score") == 5 and fake.calls.count("b7_grid_remove") == 7

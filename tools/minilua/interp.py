@@ -533,6 +533,7 @@ class Interpreter:
         self.stdout = stdout if stdout is not None else sys.stdout
         self.call_depth = 0
         self.chunks = {}
+        self.file_stack = []
         from . import stdlib
         stdlib.install(self)
 
@@ -546,7 +547,12 @@ class Interpreter:
 
     def run_file(self, path, *args):
         with open(path, encoding="utf-8") as f:
-            return self.run(f.read(), path, *args)
+            text = f.read()
+        self.file_stack.append(os.path.abspath(path))       # paths.dofile / include resolve against the running file
+        try:
+            return self.run(text, path, *args)
+        finally:
+            self.file_stack.pop()
 
     # ---- calls
     def call(self, f, args, line=None):

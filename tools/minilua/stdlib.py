@@ -497,3 +497,24 @@ def install(I):
         raise LuaError("module '%s' not found:%s" % (name, "".join("\n\tno file '%s'" % t for t in tried) or "\n\tno search path matches"))
 
     G.set("require", l_require)
+
+    # ------------------------------------------------------------ paths / include (torch's `paths` package and torch.include)
+    PT = LuaTable()
+
+    def here():
+        return os.path.dirname(I.file_stack[-1]) if I.file_stack else os.getcwd()
+
+    def p_dofile(name, *a):
+        return I.run_file(os.path.join(here(), tostring(name)), *a)
+
+    PT.set("dofile", p_dofile)
+    PT.set("thisfile", lambda: I.file_stack[-1] if I.file_stack else None)
+    PT.set("dirname", lambda p_: os.path.dirname(tostring(p_)) or ".")
+    PT.set("basename", lambda p_: os.path.basename(tostring(p_)))
+    PT.set("concat", lambda *a: os.path.join(*[tostring(x) for x in a]))
+    PT.set("filep", lambda p_: os.path.isfile(tostring(p_)))
+    PT.set("dirp", lambda p_: os.path.isdir(tostring(p_)))
+    PT.set("mkdir", lambda p_: (os.makedirs(tostring(p_), exist_ok=True), True)[1])
+    G.set("paths", PT)
+    loaded.set("paths", PT)
+    G.set("include", lambda name: (p_dofile(name), None)[1])

@@ -593,6 +593,10 @@ class Tensor:
     def m_maskedSelect(self, mask):
         return self._wrap(np.ascontiguousarray(self.a[mask.a.astype(bool).reshape(self.a.shape)]))
 
+    def m_cat(self, other, dim=None):
+        d = _i(dim) if dim is not None else self.a.ndim
+        return self._wrap(np.concatenate([self.a, other.a], axis=d - 1))
+
     def m_any(self):
         return bool(np.any(self.a != 0))
 
