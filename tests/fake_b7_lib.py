@@ -200,5 +200,72 @@ class FakeB7:
         return 0
 
 
+    # ---- DNGO: basis + Bayesian linear regression head
+    def _stack(self, n_layers, dims, W, b):
+        d = _arr(dims, (n_layers + 1,), C.c_int)
+        Ws, bs = [], []
+        for l in range(n_layers):
+            wp = C.c_void_p.from_address(W + l * C.sizeof(C.c_void_p)).value
+            bp = C.c_void_p.from_address(b + l * C.sizeof(C.c_void_p)).value
+            Ws.append(_arr(wp, (int(d[l + 1]), int(d[l]))).copy())
+            bs.append(_arr(bp, (int(d[l + 1]),)).copy())
+        return Ws, bs
+
+    def b7_grid_read(self, g, first, count, out_host):
+        grid = self._get(g, "grid")
+        _arr(out_host, (count, grid["X"].shape[1]))[...] = grid["X"][first:first + count]
+        return 0
+
+    def b7_mlp_features(self, ctx, g, n_layers, dims, W, b, relu_last, out):
+        self._get(ctx, "ctx")
+        grid = self._get(g, "grid")
+        Ws, bs = self._stack(n_layers, dims, W, b)
+        Z = self.o.mlp_features(grid["X"], Ws, bs, bool(relu_last))
+        C.c_void_p.from_address(out).value = self._new({"kind": "grid", "X": Z, "live": list(grid["live"])})
+        return 0
+
+    def b7_blr_fit(self, ctx, Z0, y, N, D, hyp, S, out, info):
+        self._get(ctx, "ctx")
+        Z, yy, H = _arr(Z0, (N, D)).copy(), _arr(y, (N,)).copy(), _arr(hyp, (S, 3)).copy()
+        fits = [self.o.blr_fit(Z, yy, H[s]) for s in range(S)]
+        if info:
+            _arr(info, (S,), C.c_int)[...] = 0
+        C.c_void_p.from_address(out).value = self._new({"kind": "blr", "fits": fits, "D": D})
+        return 0
+
+    def b7_blr_predict(self, blr, s, Z1, M, mean, var):
+        f = self._get(blr, "blr")
+        mu, v = self.o.blr_predict(f["fits"][s], _arr(Z1, (M, f["D"])).copy())
+        _arr(mean, (M,))[...] = mu
+        _arr(var, (M,))[...] = v
+        return 0
+
+    def b7_dngo_score(self, blr, g, n_layers, dims, W, b, relu_last, kind, tradeoff, bound, sign, fmin, score_host, argmax,
+                      argmax_original, best, nan_count):
+        f, grid = self._get(blr, "blr"), self._get(g, "grid")
+        Ws, bs = self._stack(n_layers, dims, W, b)
+        Z1 = self.o.mlp_features(grid["X"][grid["live"]], Ws, bs, bool(relu_last))
+        per = []
+        for fit in f["fits"]:
+            mu, v = self.o.blr_predict(fit, Z1)
+            per.append(self.o.ei_compute(mu, v, fmin, tradeoff) if kind == 0 else
+                       self.o.cb_compute(mu, v, tradeoff, "upper" if bound == 1 else "lower", sign))
+        score = self.o.mc_average(np.array(per))
+        bst, idx, nans = self.o.argmax_first(score)
+        if score_host:
+            _arr(score_host, (len(score),))[...] = score
+        C.c_int64.from_address(argmax).value = idx
+        if argmax_original:
+            C.c_int64.from_address(argmax_original).value = grid["live"][idx - 1] + 1 if idx else 0
+        C.c_double.from_address(best).value = bst
+        C.c_int64.from_address(nan_count).value = nans
+        return 0
+
+    def b7_blr_free(self, blr):
+        self._get(blr, "blr")
+        self.freed.append(("blr", blr))
+        del self.handles[blr]
+
+
 class FakeError(Exception):
     pass

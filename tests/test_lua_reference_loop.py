@@ -54,6 +54,40 @@ end
 """
 
 
+# nnTools (the network builder / trainer of the reference's DNGO) is out of scope and needs nn's backward pass, optim and
+# torch.Timer: stand-ins with the call signatures models/dngo.lua uses.  The "trained" network is a fixed random Linear / ReLU
+# stack; training is a forward pass (so that every module has an output, which dngo:init reads to find the basis layer).
+NNTOOLS = r"""
+local function builder(config, data)
+  local d = data.xr:size(2)
+  return nn.Sequential():add(nn.Linear(d, 12)):add(nn.ReLU()):add(nn.Linear(12, 20)):add(nn.ReLU()):add(nn.Linear(20, 1))
+end
+local trained = 0
+local function trainer(network, data, config, cache)
+  network:forward(data.xr)
+  cache.state.dfdx = cache.state.dfdx or torch.zeros(1)
+  trained = trained + 1
+  return {loss = 0, err = 0}
+end
+package.loaded['bot7.nnTools.builder']   = builder
+package.loaded['bot7.nnTools.trainer']   = trainer
+package.loaded['bot7.nnTools.evaluator'] = function() return 0, 0 end
+package.loaded['bot7.nnTools.buffers']   = function(config, data) return {} end
+function nnTools_trained() return trained end
+nn.MSECriterion = function() return {} end
+optim = package.loaded['optim']        -- models/dngo.lua:34 reads the global
+optim.sgd = function() end
+-- gp.models.bayes_linear: constructed by dngo:init (models/dngo.lua:74) and never used by the override
+do
+  gp = gp or {models = {}}
+  local B = torch.class('gp.models.bayes_linear')
+  function B:__init(...) end
+  function B:init(X, Y) end
+  package.loaded['gp.models'].bayes_linear = B
+end
+"""
+
+
 class Runtime:
     def __init__(self, oracle, seed=7):
         from fake_b7_lib import FakeB7
@@ -81,12 +115,11 @@ class Runtime:
         tablex.set("find", find)
         loaded.set("pl.tablex", tablex)
         loaded.set("gp.models", LuaTable())                 # the absent rock: an empty module table
-        for n in ("builder", "trainer", "evaluator", "buffers"):
-            loaded.set("bot7.nnTools." + n, LuaTable())
         for n in ("optim", "xlua"):
             loaded.set(n, LuaTable())
         loaded.set("nn", I.G.get("nn"))
         I.run(CMDLINE, "=torch.CmdLine")
+        I.run(NNTOOLS, "=nnTools stand-ins")
         self.fake = FakeB7(oracle)
         self.ffi = ffi_mod.Runtime(I, lambda name: self.fake)
         self.ffi.install()
@@ -173,3 +206,53 @@ return bot.observed, bot.responses, bot.model.hyp, bot.candidates:size(1)
     assert len(set(rows)) == 7
     assert [s[2] for s in seen] == list(range(0, 8))
     assert fake.calls.count("b7_acq_score") == 5 and fake.calls.count("b7_grid_remove") == 7
+
+
+def test_reference_dngo_class_and_bot_drive_the_glue_override(rt, oracle):
+    """models/dngo.lua (reference, unmodified) is the parent of the glue's DNGO class: its __init / init build the network, find
+    the basis layer and set config.zDim; the override's predict / acquire hand the basis stack and the BLR head to the library;
+    bots/bayesopt.lua reaches it through model:class() == 'bot7.models.dngo' (:65).  nnTools is a stand-in (see NNTOOLS)."""
+    I, fake = rt.I, rt.fake
+    g = np.random.default_rng(1)
+    X0, X1 = g.random((30, 2)), g.random((400, 2))
+    y0 = oracle.braninhoo(X0)
+    y0 = (y0 - y0.mean()) / y0.std()
+    for name, v in (("X0", X0), ("Y0", y0.reshape(-1, 1)), ("X1", X1)):
+        I.G.set(name, torch7.Tensor(np.ascontiguousarray(v), "torch.DoubleTensor"))
+    r = I.run(r"""
+local cfg = {model = {}, update = {schedule = {batchsize = 8}}, predictor = {}}
+local model = bot7.models.dngo(cfg, nil, X0, Y0)
+assert(torch.type(model) == 'bot7_b200.models.dngo' and model:class() == 'bot7.models.dngo')
+assert(model.config.zDim == 20 and torch.type(model.basis) == 'nn.ReLU' and model.basis == model.network:get(4))
+local before = nnTools_trained()
+local p = model:predict(X0, Y0, X1, nil, {mean = true, var = true})
+local net = model.network
+return p.mean, p.var, nnTools_trained() - before, net:get(1).weight, net:get(1).bias, net:get(3).weight, net:get(3).bias
+""", "=dngo predict")
+    W1, b1, W2, b2 = (t.a for t in r[3:7])
+    Z0 = oracle.mlp_features(X0, [W1, W2], [b1, b2], True)
+    Z1 = oracle.mlp_features(X1, [W1, W2], [b1, b2], True)
+    fit = oracle.blr_fit(Z0, y0, [0.0, np.log(1e2), float(y0.mean())])
+    mr, vr = oracle.blr_predict(fit, Z1)
+    assert r[2] == 1                                                   # the parent's network update ran once (models/dngo.lua:126-153)
+    assert np.allclose(r[0].a[:, 0], mr, rtol=1e-10, atol=1e-12) and np.allclose(r[1].a[:, 0], vr, rtol=1e-10, atol=1e-12)
+    # the host basis went through the reference's own minibatch loop (batchsize 8 over 30 rows) and the network's forward
+    assert fake.calls.count("b7_blr_fit") == 1 and fake.calls.count("b7_mlp_features") == 1 and fake.calls.count("b7_blr_predict") == 1
+
+    # a whole experiment with the DNGO model under the reference's bot
+    r = I.run(r"""
+local benchmarks = require('bot7.benchmarks')
+local hypers = {bot7.hyperparam('x1', 0, 1), bot7.hyperparam('x2', 0, 1)}
+local expt = {xDim = 2, yDim = 1, bot = {type = 'bo', nInitial = 3, budget = 7, verbose = 0},
+              model = {type = 'dngo', model = {}, update = {schedule = {batchsize = 4}}, predictor = {}},
+              grid = {type = 'sobol', size = 150}, score = {type = 'expected_improvement'}}
+local bot = bot7.bots.bayesopt(benchmarks.braninhoo, hypers, expt)
+assert(torch.type(bot.model) == 'bot7_b200.models.dngo')
+for t = 1, 7 do bot:run_trial() end
+return bot.observed, bot.responses, bot.candidates, bot
+""", "=dngo experiment")
+    obs, resp, cand = r[0].a, r[1].a, r[2].a
+    assert obs.shape == (7, 2) and cand.shape == (143, 2) and np.allclose(resp[:, 0], oracle.braninhoo(obs), rtol=1e-14, atol=0.0)
+    assert fake.calls.count("b7_dngo_score") == 4                       # trials 4 .. 7: one fused pass over the device grid each
+    grids = [o for o in fake.handles.values() if o["kind"] == "grid" and o["X"].shape == (150, 2)]
+    assert len(grids) == 1 and np.array_equal(cand, grids[0]["X"][grids[0]["live"]])
