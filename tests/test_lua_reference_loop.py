@@ -256,3 +256,16 @@ return bot.observed, bot.responses, bot.candidates, bot
     assert fake.calls.count("b7_dngo_score") == 4                       # trials 4 .. 7: one fused pass over the device grid each
     grids = [o for o in fake.handles.values() if o["kind"] == "grid" and o["X"].shape == (150, 2)]
     assert len(grids) == 1 and np.array_equal(cand, grids[0]["X"][grids[0]["live"]])
+
+
+@pytest.mark.parametrize("extra, acq_calls", [(["-score", "ucb"], 4), (["-bot", "rs"], 0), (["-benchmark", "hartmann6", "-noisy", "true"], 4)])
+def test_reference_example_script_variants(rt, extra, acq_calls):
+    """The same script with its other switches: the confidence bound, the random-search bot (which the glue leaves alone apart
+    from the Sobol grid it draws from), a 6-dimensional noisy objective."""
+    I, fake = rt.I, rt.fake
+    argv = ["-budget", "6", "-grid_size", "120", "-nInitial", "2", "-verbose", "0"] + extra
+    I.G.set("arg", LuaTable({k + 1: v for k, v in enumerate(argv)}))
+    I.run_file(os.path.join(REF, "examples", "run_benchmark.lua"))
+    assert "Error" not in rt.out.getvalue()
+    assert fake.calls.count("b7_sobol_generate") == 1 and fake.calls.count("b7_acq_score") == acq_calls
+    assert fake.calls.count("b7_grid_remove") == (6 if acq_calls else 0)
