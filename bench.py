@@ -18,7 +18,7 @@ e2e    : the same through the C ABI with HOST buffers: b7_gp_fit_sharded (X, y, 
 multi  : one process per GPU (torchrun); everything that crosses GPUs runs inside libbot7_b200.so (b7_comm_init_rank,
          b7_gp_fit_sharded, b7_acq_score_multi: NCCL over NVLink); torch.distributed (gloo) only carries the 128-byte
          NCCL id, the barriers and the max over ranks of the timings.
-Launch : python bench.py --gpus N --steps K --warmup W [--config headline|c2|c3|c4|c5] [--scaling weak|strong]
+Launch : python bench.py --gpus N --steps K --warmup W [--config headline|c1|c2|c3|c4|c5] [--scaling weak|strong]
          python bench.py --impl reference ...     (CPU arm: the oracle port on the host cores, same config)
 Prints ONE JSON line on rank 0; exits 3 if the two posterior paths select different candidates.
 """
@@ -49,6 +49,8 @@ EI, CB = 0, 1
 CONFIGS = {
     "headline": dict(N=4096, d=6, S=32, kind=EI, obj="hartmann6", M=M_STEP, scaling="weak",
                      workload="Hartmann6 integrated EI, N_obs=4096, d=6, S=32 draws (headline of BASELINE.json metric; fits one GPU)"),
+    "c1": dict(N=50, d=2, S=10, kind=EI, obj="braninhoo", M=20000, scaling="weak",
+               workload="config 1: examples/run_benchmark.lua shape -- Branin-Hoo 2D, bayesopt EI, GP ARD-SE, N=50 obs, S=10 draws, 20k Sobol candidates"),
     "c2": dict(N=512, d=6, S=1, kind=CB, obj="hartmann6", M=1 << 20, scaling="weak",
                workload="config 2: Hartmann6 6D, UCB (-LCB, kappa=1), single MAP GP, N=512 obs, 2^20 Sobol candidates per GPU"),
     "c3": dict(N=2048, d=6, S=32, kind=EI, obj="hartmann6", M=1 << 22, scaling="strong",
@@ -114,8 +116,14 @@ def dngo_basis(d, D):
     return z[:d * D].reshape(d, D), z[d * D:]
 
 
+def braninhoo(X):
+    """benchmarks/braninhoo.lua:21-44 on [-5, 10] x [0, 15] mapped from the unit square (restated; only synthesises Y_obs)."""
+    x1, x2 = 15.0 * X[:, 0] - 5.0, 15.0 * X[:, 1]
+    return (x2 - 5.1 / (4 * np.pi ** 2) * x1 ** 2 + 5.0 / np.pi * x1 - 6.0) ** 2 + 10.0 * (1 - 1.0 / (8 * np.pi)) * np.cos(x1) + 10.0
+
+
 def objective(cfg, X):
-    y = hartmann6(X) if cfg["obj"] == "hartmann6" else ackley(X)
+    y = {"hartmann6": hartmann6, "braninhoo": braninhoo}.get(cfg["obj"], ackley)(X)
     return (y - y.mean()) / y.std()
 
 
