@@ -68,12 +68,6 @@ def lua_pattern_to_re(pat):
     return "".join(out)
 
 
-def _captures(m, whole_if_none=True):
-    if m.re.groups == 0:
-        return [m.group(0)] if whole_if_none else []
-    return [g if g != "" or True else g for g in m.groups()]
-
-
 _FMT = re.compile(r"%([-+ #0]*)(\d*)(?:\.(\d+))?([cdiouxXeEfgGqs%])")
 
 
