@@ -280,6 +280,19 @@ def slices_bytes_per_draw(Np):
 
 # ------------------------------------------------------------------ GPU arm
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout (main() points file descriptor 1 at stderr for everything else)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,8 +319,16 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    # NCCL's own log lines (the version banner at NCCL_DEBUG=WARN / VERSION, INFO lines) go to stderr: stdout carries ONE JSON line
+    # NCCL's own log lines (the version banner at NCCL_DEBUG=WARN / VERSION, INFO lines) go to stderr: stdout carries ONE JSON line.
+    # NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION becomes WARN (which prints the banner too); and because
+    # a library may still write to file descriptor 1 directly, the descriptor itself points at stderr until the line is printed.
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     from bot7_b200 import _lib as L
     from bot7_b200 import models, parallel
     dist = None
@@ -582,7 +603,7 @@ def main():
         line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
                                 "fit_ms_per_factor": c["fit_ms_per_factor"], "scoring_gflops": c["gflops"],
                                 "note": "CPU restatement (Torch7/gpTorch7 unavailable)"}
-    print(json.dumps(line))
+    emit(line)
     comm.free_fit(state["gps"])
     if dist:
         dist.destroy_process_group()
@@ -696,7 +717,7 @@ def bench_dngo(args, cfg, comm, ctx, L, lib, models, parallel, dist, pk, Xo, y, 
         c = cpu_sample(cfg)
         line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port", "sample": c["sample"],
                                 "fit_ms_per_factor": c["fit_ms_per_factor"], "note": "CPU restatement (Torch7/gpTorch7 unavailable)"}
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
