@@ -479,11 +479,16 @@ trail_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, in
 // ---- row-sliced variants for one or two factors ----------------------------------------------------
 // With a single factor a block column offers at most 31 tiles: one CTA per tile leaves most SMs idle for the ~17 us a
 // 128 x 128 x 128 product takes on one SM's DMMA pipe, and the k = 512 updates hold an SM for ~70 us while the chain's
-// next kernel waits for a free one.  Here a CTA owns SL_ROWS = 32 rows of a tile (4 CTAs per tile): the B operand
-// streams as whole 16 KB k-tiles, the A operand as the 4 x 1 KB row runs of its k-tile.  Every output element sees the
+// next kernel waits for a free one.  Here a CTA owns SL_ROWS rows of a tile (first 32 rows = 4 CTAs per tile, now 16 = 8 CTAs per
+// tile, see below): the B operand streams as whole 16 KB k-tiles, the A operand as the 4 row runs of its k-tile.  Every output element sees the
 // same DMMA sequence (k ascending, one accumulator) and the beta reduction keeps the order of panel_kernel, so the
 // results are bit-identical to the tile kernels.  Warp (wm, wn) owns rows 16 wm.., columns 32 wn.. : 2 x 4 fragments.
-constexpr int SL_ROWS = 32, SL_STAGES = 8, SL_AHEAD = 6;
+// Second step: SL_ROWS = 16 with 4 warps per CTA (8 CTAs per tile; N = 4096 refit 2.04 -> 1.99 ms, N = 2048 0.85 -> 0.82).  A warp keeps exactly the fragment shape and
+// the instruction sequence it had with 32-row slices (16 rows x 32 columns), so every output element and every partial of the
+// beta reduction is computed by the same operations in the same order -- only the DMMA time of a CTA halves (one warp per
+// sub-core, 256 DMMAs = 4096 cycles per k = 128 product).  6 stages of 18 KB leave room for two CTAs per SM, so that the
+// 8 x 31 CTAs of the first block columns at N = 4096 are one wave.
+constexpr int SL_ROWS = 16, SL_STAGES = 6, SL_AHEAD = 5, SL_THREADS = (SL_ROWS / 16) * 128, SL_SPLIT = NBK / SL_ROWS;
 constexpr int SL_A_DOUBLES = SL_ROWS * TILE_K;                     // 512
 constexpr int SL_STAGE_DOUBLES = TILE_DOUBLES + SL_A_DOUBLES;      // B tile then A slice: 20 KB
 constexpr int SL_SMEM = SL_STAGES * SL_STAGE_DOUBLES * 8 + 256;    // + 2 * SL_STAGES barriers
@@ -500,12 +505,12 @@ struct SliceRing {
     empty = full + SL_STAGES;
     issued = consumed = 0;
     if (threadIdx.x == 0) {
-      for (int st = 0; st < SL_STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, THREADS / 32); }
+      for (int st = 0; st < SL_STAGES; ++st) { mbar_init(full + st, 1); mbar_init(empty + st, SL_THREADS / 32); }
       mbar_fence_init();
     }
     __syncthreads();
   }
-  // thread 0: k-tile of B (128 rows) and rows r0 .. r0 + 31 of the matching k-tile of A
+  // thread 0: k-tile of B (128 rows) and rows r0 .. r0 + SL_ROWS - 1 of the matching k-tile of A
   __device__ __forceinline__ void produce(const double* a_tile, const double* b_tile, int r0) {
     const int slot = issued % SL_STAGES;
     if (issued >= SL_STAGES) mbar_wait(empty + slot, (unsigned)(((issued / SL_STAGES) - 1) & 1));
@@ -557,7 +562,7 @@ __device__ __forceinline__ void slice_mainloop(SliceRing& ring, const double* __
 __device__ __forceinline__ int sl_row(int wm, int i, int lane) { return 16 * wm + 8 * i + (lane >> 2); }
 
 // panel: L21 = A21 * inv(L11)^T and beta_i -= L21 x_j, rows r0 .. r0 + 31 of tile it = j + 1 + blockIdx.y
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(SL_THREADS, 2)
 panel_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j, const double* __restrict__ dinv,
                    long long dinv_stride, double* __restrict__ beta, int s0) {
   extern __shared__ __align__(128) double smem[];
@@ -575,7 +580,7 @@ panel_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j
   slice_mainloop(ring, tile, B, KPB, r0, acc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wm = warp >> 2, wn = warp & 3;
   const double* xj = beta + (long long)s * Np + j * NBK;
-  double* red = smem;   // [32][4]
+  double* red = smem;   // [SL_ROWS][4]
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int row = sl_row(wm, i, lane);
@@ -599,10 +604,10 @@ panel_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int j
 
 // trailing update: C[it][nt] -= L[it][kb0:kb1] L[nt][kb0:kb1]^T, rows r0 .. r0 + 31 of the tile;
 // it = it0 + blockIdx.x / 4, nt = nt0 + blockIdx.y (tiles above the diagonal exit at once)
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(SL_THREADS, 2)
 trail_slice_kernel(double* __restrict__ fac, long long fac_stride, int Np, int kb0, int kb1, int it0, int nt0, int s0) {
   extern __shared__ __align__(128) double smem[];
-  const int it = it0 + (blockIdx.x >> 2), nt = nt0 + blockIdx.y, r0 = (blockIdx.x & 3) * SL_ROWS;
+  const int it = it0 + (int)(blockIdx.x / SL_SPLIT), nt = nt0 + blockIdx.y, r0 = (int)(blockIdx.x % SL_SPLIT) * SL_ROWS;
   pdl_trigger();
   if (nt > it) { pdl_wait(); return; }     // (a CTA that left without waiting would let the grid complete before its predecessor)
   const int s = s0 + blockIdx.z, KPB = NBK / TILE_K, KTA = Np / TILE_K;
@@ -926,7 +931,7 @@ int potrf_latency_enqueue(b7_gp* gp, int s0, int count, int W, bool allow_trace)
   trace.mark("start");
   // kernels of the main stream follow their predecessor programmatically; the side and far streams launch normally
   auto trail = [&](cudaStream_t st, int kb0, int kb1, int it0, int n_it, int nt0, int n_nt) {
-    launch_pdl(trail_slice_kernel, dim3(n_it * SPT, n_nt, count), dim3(THREADS), SL_SMEM, st, pdl && st == sa, gp->fac, fs, Np, kb0, kb1, it0, nt0, s0);
+    launch_pdl(trail_slice_kernel, dim3(n_it * SPT, n_nt, count), dim3(SL_THREADS), SL_SMEM, st, pdl && st == sa, gp->fac, fs, Np, kb0, kb1, it0, nt0, s0);
     b7_count(ctx);
   };
   for (int J = 0; J < NB; J += W) {
@@ -938,7 +943,7 @@ int potrf_latency_enqueue(b7_gp* gp, int s0, int count, int W, bool allow_trace)
       trace.mark("diag");
       const int rem = NB - 1 - j;
       if (rem > 0) {
-        launch_pdl(panel_slice_kernel, dim3(SPT, rem, count), dim3(THREADS), SL_SMEM, sa, pdl, gp->fac, fs, Np, j, (const double*)gp->dinv, ds, gp->beta, s0);
+        launch_pdl(panel_slice_kernel, dim3(SPT, rem, count), dim3(SL_THREADS), SL_SMEM, sa, pdl, gp->fac, fs, Np, j, (const double*)gp->dinv, ds, gp->beta, s0);
         b7_count(ctx);
         trace.mark("panel");
       }
