@@ -1013,7 +1013,12 @@ int b7_launch_potrf(b7_gp* gp, int s0, int count) {
   const int W = W_env > 0 ? W_env : 4;   // outer panel = 4 blocks (512 columns)
   // one or two factors: the latency-oriented schedule with row-sliced kernels (bit-identical results)
   static const int slice_env = getenv("B7_POTRF_SLICE") ? atoi(getenv("B7_POTRF_SLICE")) : -1;
-  if (slice_env >= 0 ? slice_env != 0 : count <= 2) return potrf_latency(gp, s0, count, W);
+  // ... and small batches of small factors, where the machine is as empty (tools/refit_vs_s.py, refit ms batched -> latency
+  // schedule: N = 512, 8 draws 0.385 -> 0.273; N = 2048, 4 draws 1.68 -> 1.15, 8 draws 2.09 -> 1.72, 16 draws 2.78 -> 2.94;
+  // N = 4096, 4 draws 4.46 -> 4.83): up to S NB^2 = 2048 tile columns.  The test looks at the handle's total number of draws,
+  // like the INT8 / FP64 choice below (which starts at 4096), so a sharded fit and the one-GPU fit take the same arithmetic.
+  const bool small_batch = (long long)gp->S * NB * NB <= 2048;
+  if (slice_env >= 0 ? slice_env != 0 : (count <= 2 || small_batch)) return potrf_latency(gp, s0, count, W);
   cudaStream_t sa = ctx->stream, sb = ctx->stream2;
   bool far_pending = false;
   PotrfTrace trace;
