@@ -85,6 +85,8 @@ print(pcall(function() return 1 + {} end))
 print(pcall(function() return #5 end))
 print(pcall(function() local f; f() end))
 print(tostring(nil), tostring(true), tostring(12), 1 .. 2, 'a' .. 1.5)
+print(-2^2, 2^3^2, not 1 == 2, 1 .. 2 .. 3, 2 * 3 % 4, -3 % 5, 1 + 2 < 4 and 'y' or 'n', #'ab' + 1, -2 ^ -2, -0.0, 100 * 1.1, 1e16)
+for i = 1, 2, 0.5 do io.write(i, ';') end print()
 return 'done', 42
 """
 
@@ -124,6 +126,8 @@ false\tattempt to perform arithmetic on a table value
 false\tattempt to get length of a number value
 false\tattempt to call 'f' (a nil value)
 nil\ttrue\t12\t12\ta1.5
+-4\t512\tfalse\t123\t2\t2\ty\t3\t-0.25\t-0\t110\t1e+16
+1;1.5;2;
 """
 
 

@@ -129,7 +129,7 @@ def fmt_number(v):
     if v in (math.inf, -math.inf):
         return "inf" if v > 0 else "-inf"
     if v.is_integer() and abs(v) < 1e15:
-        return str(int(v))
+        return "-0" if v == 0 and math.copysign(1.0, v) < 0 else str(int(v))      # printf("%.14g", -0.0)
     return "%.14g" % v
 
 
