@@ -24,6 +24,9 @@ function model:__init(config)
   config['nSamples']   = config.nSamples  or 1
   config['prior_std']  = config.prior_std or 2.0     -- declared: independent N(0, prior_std^2) on every hyp entry
   config['spec_width'] = config.spec_width or 8      -- density evaluations per batched device call
+  -- batched density evaluations through sampler_spec.lua: the chain of bot7.samplers.slice from the same generator state,
+  -- in fewer device calls (false: the reference sampler, one evaluation per call)
+  if config.speculative == nil then config['speculative'] = true end
   -- declared initial state of the chain (model:init); gpTorch7's own values are unknown
   config['init_lengthscale'] = config.init_lengthscale or 0.5
   config['init_sigma_f']     = config.init_sigma_f or 1.0
@@ -132,13 +135,24 @@ end
 -- bot7.samplers.slice (samplers/slice.lua, unchanged) drives the chain; each f(x) is one density evaluation on the GPU.
 function model:sample_hypers(X, Y, _, _, single)
   if self.hyp == nil then self:init(X, Y) end
-  local n       = single and 1 or self.config.nSamples
-  local sampler = bot7.samplers[self.config.sampler]()
-  local f       = function(x, args) return self:log_density(x, X, Y) end
-  local out     = torch.DoubleTensor(n, self.hyp:nElement())
-  local x       = self.hyp:view(1, -1):clone()
+  local n    = single and 1 or self.config.nSamples
+  local spec = self.config.speculative and self.config.sampler == 'slice'
+  local sampler, f
+  if spec then
+    sampler = require('bot7_b200.sampler_spec')()
+    f       = function(V, args) return self:log_density_batch(V, X, Y) end
+  else
+    sampler = bot7.samplers[self.config.sampler]()
+    f       = function(x, args) return self:log_density(x, X, Y) end
+  end
+  local out = torch.DoubleTensor(n, self.hyp:nElement())
+  local x   = self.hyp:view(1, -1):clone()
   for i = 1, n do
-    x = sampler(f, x, {nSamples = 1}, nil)
+    if spec then
+      x = sampler(f, x, {nSamples = 1}, nil, self.config.spec_width)
+    else
+      x = sampler(f, x, {nSamples = 1}, nil)
+    end
     out[i]:copy(x[1])
   end
   self.hyp = out[n]:view(1, -1):clone()

@@ -420,6 +420,45 @@ return p.mean, p.var, one.mean, one.var, ld, ldb, ld2, ldbad, ei, start, draws, 
 
 
 @pytest.mark.gpu
+def test_lua_speculative_hyper_sampling_matches_the_python_twin(oracle):
+    """model:sample_hypers through lua/bot7_b200/sampler_spec.lua (batches of 8 density evaluations per b7_gp_refit) against the
+    Python twin's slice_speculative on the same device library: both draw from numpy generators with the same seed in the same
+    order, so the chains coincide (to the rounding of the direction's norm), and the sequential setting gives the same chain."""
+    if not _has_gpu():
+        pytest.skip("no CUDA device")
+    sys.path.insert(0, ROOT)
+    from bot7_b200 import models
+    Xo, y, hyp, _ = problem(oracle, 200, 2, 1, 10)
+
+    def lua_chain(speculative):
+        r_ = GlueRuntime(seed=9)
+        r_.run("require('bot7_b200').install()")
+        for name, v in [("X0", Xo), ("Y0", y.reshape(-1, 1)), ("H0", hyp[:1])]:
+            r_.set_global(name, r_.tensor(v))
+        r_.set_global("SPEC", speculative)
+        r = r_.run(r"""
+local model = bot7.models.gp_regressor{kernel = 'ardse', nSamples = 5, speculative = SPEC, spec_width = 8}
+model.hyp = H0:clone()
+local draws = model:sample_hypers(X0, Y0)
+return draws, model.hyp, torch.rand(1)[1]
+""")
+        out = (r[0].a.copy(), r[1].a.copy(), r[2], list(r_.ffi.calls))
+        r_.close()
+        return out
+    spec, spec_state, spec_next, _ = lua_chain(True)
+    tw = models.gp_regressor({"kernel": "ardse", "nSamples": 5, "speculative": True, "spec_width": 8}, rng=np.random.default_rng(9))
+    tw.hyp = hyp[0].copy()
+    ref = tw.sample_hypers(Xo, y)
+    assert spec.shape == (5, 5) and np.allclose(spec, ref, rtol=0.0, atol=1e-9)
+    assert np.allclose(spec_state[0], tw.hyp, rtol=0.0, atol=1e-9)
+    assert abs(spec_next - tw.rng.random()) == 0.0                       # both generators were left in the same state
+    # the fixture's sequential stand-in sampler draws in another order, so the sequential setting is compared through the twin
+    tw2 = models.gp_regressor({"kernel": "ardse", "nSamples": 5, "speculative": False}, rng=np.random.default_rng(9))
+    tw2.hyp = hyp[0].copy()
+    assert np.array_equal(tw2.sample_hypers(Xo, y), ref)
+
+
+@pytest.mark.gpu
 def test_lua_bayesopt_nominates_the_oracle_argmax(rt, oracle):
     Xo, y, hyp, Xc = problem(oracle, 120, 2, 1, 3000)
     for name, v in [("X0", Xo), ("Y0", y.reshape(-1, 1)), ("XC", Xc)]:
@@ -579,3 +618,45 @@ return out, evals, gibbs, torch.type(sampler)
     assert 0.6 < xs[:, 0].var() < 1.6 and 2.4 < xs[:, 1].var() < 6.4          # N(0, diag(1, 4)); 400 correlated draws
     assert gibbs.shape == (3, 2) and np.isfinite(gibbs).all()
     assert "Error" not in out.getvalue()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("width", [1, 3, 4, 8])
+def test_lua_speculative_sampler_walks_the_executed_reference_chain(width):
+    """lua/bot7_b200/sampler_spec.lua (batched density evaluations, generator rewound after discarded speculation) against
+    the reference's samplers/slice.lua executed next to it: from the same generator state the two chains are bit-identical,
+    for every batch width, with step-out, with a narrow initial bracket (stepping out needed) and a wide one (shrinking)."""
+    def chain(speculative):
+        rt = GlueRuntime(seed=11, fixture=False)
+        I = rt.I
+        I.run("bot7 = {samplers = {}, utils = {}}")
+        ut = I.run_file(os.path.join(REF, "utils", "tensor.lua"))[0]
+        I.G.get("bot7").get("utils").set("tensor", ut)
+        I.G.get("package").get("loaded").set("bot7.utils", I.G.get("bot7").get("utils"))
+        I.run_file(os.path.join(REF, "samplers", "abstract.lua"))
+        I.run_file(os.path.join(REF, "samplers", "slice.lua"))
+        I.G.set("SPEC", speculative)
+        I.G.set("WIDTH", width)
+        r = I.run(r"""
+local evals, calls = 0, 0
+local function logp1(x, a) return -0.5 * (x[1] ^ 2 / a.v1 + x[2] ^ 2 / a.v2 + 0.3 * x[1] * x[2]) end
+local function f(x, a) evals = evals + 1; return logp1(x[1], a) end
+local function fb(P, a) calls = calls + 1; local o = torch.Tensor(P:size(1)); for i = 1, P:size(1) do evals = evals + 1; o[i] = logp1(P[i], a) end; return o end
+local sampler = SPEC and require('bot7_b200.sampler_spec')() or bot7.samplers.slice()
+local out, x = torch.Tensor(120, 2), torch.Tensor{{0.3, -0.2}}
+for i = 1, 120 do
+  local opt = {nSamples = 1, width = (i % 2 == 0) and 0.05 or 6.0}        -- narrow brackets step out, wide ones shrink
+  if SPEC then x = sampler(fb, x, opt, {v1 = 1.0, v2 = 4.0}, WIDTH) else x = sampler(f, x, opt, {v1 = 1.0, v2 = 4.0}) end
+  out[i]:copy(x[1])
+end
+return out, evals, calls, torch.rand(1)[1]
+""")
+        rt.close()
+        return r[0].a, r[1], r[2], r[3]
+    ref, ref_evals, _, ref_next = chain(False)
+    got, evals, calls, nxt = chain(True)
+    assert np.array_equal(got, ref)                       # the same chain, bit for bit
+    assert nxt == ref_next                                # and the generator is left where the sequential sampler leaves it
+    assert calls < ref_evals                              # in fewer sequential (device) calls
+    if width >= 4:
+        assert calls < 0.5 * ref_evals

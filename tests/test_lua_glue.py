@@ -234,6 +234,7 @@ TORCH7_METHODS = {
     "isSameSizeAs", "le", "log", "long", "lt", "max", "mean", "min", "mm", "mul", "mv", "nDimension", "nElement", "narrow", "ne", "neg",
     "norm", "numel", "pow", "prod", "repeatTensor", "reshape", "resize", "resizeAs", "select", "set", "size", "sort", "sqrt", "squeeze",
     "std", "storage", "stride", "sub", "sum", "t", "transpose", "type", "typeAs", "unfold", "var", "view", "viewAs", "zero",
+    "any", "all", "maskedCopy", "maskedFill", "maskedSelect", "nonzero", "indexFill", "cat", "clamp", "cdiv", "cpow",
     "forward", "evaluate", "training", "get", "parameters", "getParameters", "updateOutput",
     "find", "format", "gmatch", "gsub", "len", "lower", "match", "rep", "sub", "upper",
 }

@@ -183,7 +183,7 @@ local benchmarks = require('bot7.benchmarks')
 local hypers = {bot7.hyperparam('x1', 0, 1), bot7.hyperparam('x2', 0, 1)}
 local expt = {xDim = 2, yDim = 1,
               bot = {type = 'bo', nInitial = 2, budget = 7, nSamples = 3, verbose = 0},
-              model = {noiseless = true, nSamples = 2},
+              model = {noiseless = true, nSamples = 2, speculative = false},   -- the reference's own slice sampler over the glue's density
               grid = {type = 'sobol', size = 200},
               score = {type = 'confidence_bound', tradeoff = 1.5}}
 local bot = bot7.bots.bayesopt(benchmarks.braninhoo, hypers, expt)
@@ -206,6 +206,7 @@ return bot.observed, bot.responses, bot.model.hyp, bot.candidates:size(1)
     assert len(set(rows)) == 7
     assert [s[2] for s in seen] == list(range(0, 8))
     assert fake.calls.count("b7_acq_score") == 5 and fake.calls.count("b7_grid_remove") == 7
+    assert fake.calls.count("b7_gp_refit") > 100                      # one device call per density evaluation of samplers/slice.lua
 
 
 def test_reference_dngo_class_and_bot_drive_the_glue_override(rt, oracle):

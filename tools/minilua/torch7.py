@@ -590,6 +590,15 @@ class Tensor:
         self.a[mask.a.astype(bool).reshape(self.a.shape)] = val
         return self
 
+    def m_maskedCopy(self, mask, src):
+        self._writable()
+        m = mask.a.astype(bool).reshape(self.a.shape)
+        n = int(m.sum())
+        if src.a.size < n:
+            raise LuaError("maskedCopy: the source has fewer elements than the mask selects")
+        self.a[m] = src.a.ravel()[:n]
+        return self
+
     def m_maskedSelect(self, mask):
         return self._wrap(np.ascontiguousarray(self.a[mask.a.astype(bool).reshape(self.a.shape)]))
 
@@ -739,6 +748,22 @@ def install(I, seed=0):
     def t_seed(s=0):
         state["rng"] = np.random.default_rng(_i(s))
 
+    class RNGState:
+        lua_type = "userdata"
+
+        def __init__(self, st):
+            self.st = st
+
+    def t_get_state():
+        import copy
+        return RNGState(copy.deepcopy(state["rng"].bit_generator.state))
+
+    def t_set_state(st):
+        import copy
+        if not isinstance(st, RNGState):
+            raise LuaError("setRNGState: a state returned by torch.getRNGState() expected")
+        state["rng"].bit_generator.state = copy.deepcopy(st.st)
+
     def t_cat(*a):
         if isinstance(a[0], LuaTable):
             ts = [a[0].get(k) for k in range(1, a[0].length() + 1)]
@@ -784,7 +809,7 @@ def install(I, seed=0):
     T.set("Tensor", lambda *a: make_tensor(state["default"], a))
     for name, f in [("class", t_class), ("type", t_type), ("typename", lambda v: [typename(v)]), ("isTensor", lambda v=None: isinstance(v, Tensor)),
                     ("zeros", new_filled(0)), ("ones", new_filled(1)), ("rand", t_rand), ("randn", t_randn), ("randperm", t_randperm),
-                    ("manualSeed", t_seed), ("cat", t_cat), ("add", t_add), ("range", t_range), ("mm", t_mm),
+                    ("manualSeed", t_seed), ("getRNGState", t_get_state), ("setRNGState", t_set_state), ("cat", t_cat), ("add", t_add), ("range", t_range), ("mm", t_mm),
                     ("cmul", lambda a, b: a.m_clone().m_cmul(b)), ("cdiv", lambda a, b: a.m_clone().m_cdiv(b)),
                     ("mul", fresh("mul")), ("div", fresh("div")), ("sqrt", fresh("sqrt")), ("exp", fresh("exp")), ("log", fresh("log")),
                     ("abs", fresh("abs")), ("pow", fresh("pow")), ("neg", fresh("neg")), ("floor", fresh("floor")), ("ceil", fresh("ceil")),
