@@ -236,7 +236,12 @@ def run_reference(args, cfg, rank):
     line = {"impl": "reference", "metric": METRIC if args.config == "headline" else f"candidates scored/s ({args.config})", "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cfg["M"] / value * 1e3, "higher_is_better": True,
             "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "cpu_sample": last["sample"]},
+            # the same workload description as the GPU arm's line (its `arithmetic` and `l2` entries describe that arm and are left out);
+            # what a step of this arm actually computes is in `cpu_sample` / `cpu_baseline.sample`
+            "config": {"workload": cfg["workload"], "kernel": "ARD-SE" if "D" not in cfg else "BLR head",
+                       "candidates_per_gpu_per_step": cfg["M"] if cfg["scaling"] == "weak" else cfg["M"] // max(args.gpus, 1),
+                       "candidates_total": cfg["M"] * (args.gpus if cfg["scaling"] == "weak" else 1),
+                       "grid": "Sobol", "cpu_sample": last["sample"]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
                              "fit_ms_per_factor": last["fit_ms_per_factor"], "scoring_gflops": last["gflops"],
                              "note": "CPU restatement (Torch7/gpTorch7 unavailable: no Lua runtime, gp rock not vendored)"},
