@@ -445,7 +445,10 @@ return draws, model.hyp, torch.rand(1)[1]
         out = (r[0].a.copy(), r[1].a.copy(), r[2], list(r_.ffi.calls))
         r_.close()
         return out
-    spec, spec_state, spec_next, _ = lua_chain(True)
+    spec, spec_state, spec_next, calls = lua_chain(True)
+    # eight density evaluations per device call: one b7_gp_fit for the resident handle, then b7_gp_refit per batch
+    n_batches = calls.count("b7_gp_fit") + calls.count("b7_gp_refit")
+    assert calls.count("b7_gp_fit") == 1 and 5 <= n_batches <= 40
     tw = models.gp_regressor({"kernel": "ardse", "nSamples": 5, "speculative": True, "spec_width": 8}, rng=np.random.default_rng(9))
     tw.hyp = hyp[0].copy()
     ref = tw.sample_hypers(Xo, y)

@@ -137,8 +137,8 @@ def check_pointer_compat(val, base, depth, what):
 class CFunc:
     lua_type = "cdata"
 
-    def __init__(self, name, fn, ret, params):
-        self.name, self.fn, self.ret, self.params = name, fn, ret, params
+    def __init__(self, name, fn, ret, params, log=None):
+        self.name, self.fn, self.ret, self.params, self.log = name, fn, ret, params, log
         rb, rd = norm_type(ret)
         if rd > 0:
             fn.restype = C.c_char_p if (rb, rd) == ("char", 1) else C.c_void_p
@@ -181,6 +181,8 @@ class CFunc:
                     conv.append(int(a))            # LuaJIT truncates
                 else:
                     conv.append(float(a))
+        if self.log is not None:
+            self.log.append(self.name)
         r = self.fn(*conv)
         rb, rd = norm_type(self.ret)
         if rb == "void" and rd == 0:
@@ -205,8 +207,8 @@ class CStr:
 class CLib:
     lua_type = "userdata"
 
-    def __init__(self, dll, decls, name):
-        self.dll, self.decls, self.name, self.cache = dll, decls, name, {}
+    def __init__(self, dll, decls, name, log=None):
+        self.dll, self.decls, self.name, self.cache, self.log = dll, decls, name, {}, log
 
     def lua_index(self, key):
         if key in self.decls.enums:
@@ -220,7 +222,7 @@ class CLib:
         except AttributeError:
             raise LuaError("cannot resolve symbol '%s': undefined symbol in %s" % (key, self.name))
         ret, params = self.decls.funcs[key]
-        f = CFunc(key, fn, ret, params)
+        f = CFunc(key, fn, ret, params, self.log)
         self.cache[key] = f
         return f
 
@@ -377,7 +379,7 @@ class Runtime:
                 dll = self.lib_resolver(tostring(name))
             except OSError as e:
                 raise LuaError("cannot load library '%s': %s" % (tostring(name), e))
-            return CLib(dll, self.decls, tostring(name))
+            return CLib(dll, self.decls, tostring(name), self.calls)
 
         def f_string(p, n=None):
             if isinstance(p, CStr):
