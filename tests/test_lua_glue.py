@@ -1,11 +1,13 @@
-"""Static checks of the LuaJIT drop-in (lua/bot7_b200/*.lua).  No Lua runtime exists in the image, so the glue cannot be
-executed here; what CAN be checked on the CPU is that it is complete with respect to the reference's own call sites:
+"""Static checks of the LuaJIT drop-in (lua/bot7_b200/*.lua); its execution under tools/minilua is tests/test_lua_exec.py and
+tests/test_lua_reference_loop.py.  Checked here, without running anything: the glue is complete with respect to the reference's own
+call sites and well-formed:
 
 * every method the reference calls on the model / score / grid / sampler objects of the accelerated path
   (extracted from /root/reference when it is present, otherwise from the committed list below, which was extracted
   from it) is defined by the replacement class, or inherited from the reference parent it subclasses;
 * every C symbol the glue calls through `B.C.` is declared in include/bot7_b200.h (and therefore in the generated cdef);
-* block keywords balance (function/if/for/while/do ... end), the cheapest syntax check available without a parser.
+* block keywords balance (the first, parser-free check) and, with tools/lua_check.py, the full grammar, every name, every
+  `self:method()`, the arity of every FFI call and the existence of every method name (second half of this file).
 """
 import os
 import re
