@@ -267,5 +267,65 @@ class FakeB7:
         del self.handles[blr]
 
 
+    # ---- multi-GPU block: one process, n devices; shards are index ranges of ONE logical grid with a shared tombstone list
+    def _shards(self, M, n):
+        base, rem = divmod(M, n)
+        out, r0 = [], 0
+        for g in range(n):
+            cnt = base + (1 if g < rem else 0)
+            out.append((r0, cnt))
+            r0 += cnt
+        return out
+
+    def b7_comm_init_all(self, n_gpus, device_ids, out):
+        if n_gpus < 1:
+            raise FakeError("comm_init_all: n_gpus")
+        C.c_void_p.from_address(out).value = self._new({"kind": "comm", "n": n_gpus})
+        return 0
+
+    def b7_comm_free(self, comm):
+        self._get(comm, "comm")
+        self.freed.append(("comm", comm))
+        del self.handles[comm]
+
+    def b7_grid_from_host_sharded(self, comm, X, M, d, out_grids):
+        c = self._get(comm, "comm")
+        whole = {"X": _arr(X, (M, d)).copy(), "live": list(range(M))}          # shared by the shard handles
+        for g, (r0, cnt) in enumerate(self._shards(M, c["n"])):
+            h = self._new({"kind": "grid", "X": whole["X"], "live": whole["live"], "whole": whole, "shard": (r0, cnt)})
+            C.c_void_p.from_address(out_grids + g * C.sizeof(C.c_void_p)).value = h
+        return 0
+
+    def b7_grid_remove_sharded(self, comm, grids, idx, removed_row):
+        c = self._get(comm, "comm")
+        hs = [C.c_void_p.from_address(grids + g * C.sizeof(C.c_void_p)).value for g in range(c["n"])]
+        first = self._get(hs[0], "grid")
+        for h in hs[1:]:
+            if self._get(h, "grid")["whole"] is not first["whole"]:
+                raise FakeError("grid_remove_sharded: the handles do not belong to one sharded grid")
+        return FakeB7.b7_grid_remove(self, hs[0], idx, removed_row)
+
+    def b7_gp_fit_sharded(self, comm, kernel, X, y, N, d, hyp, S, H, noiseless, out_gps, info, logml, jitter, gather_ms):
+        c = self._get(comm, "comm")
+        gp = {"kind": "gp", "X": _arr(X, (N, d)).copy(), "y": _arr(y, (N,)).copy(), "kernel": kernel, "noiseless": bool(noiseless),
+              "S": S, "flags": 0}
+        self._fit(gp, _arr(hyp, (S, H)).copy(), info, logml, jitter)
+        for g in range(c["n"]):                                                # every device ends up with all S factors
+            C.c_void_p.from_address(out_gps + g * C.sizeof(C.c_void_p)).value = self._new(dict(gp))
+        if gather_ms:
+            C.c_double.from_address(gather_ms).value = 0.0
+        return 0
+
+    def b7_acq_score_multi(self, comm, gps, grids, kind, tradeoff, bound, sign, fmin, score_host, argmax, argmax_original, best, nan_count):
+        c = self._get(comm, "comm")
+        gh = [C.c_void_p.from_address(gps + g * C.sizeof(C.c_void_p)).value for g in range(c["n"])]
+        rh = [C.c_void_p.from_address(grids + g * C.sizeof(C.c_void_p)).value for g in range(c["n"])]
+        for h in gh:
+            self._get(h, "gp")
+        for h in rh:
+            self._get(h, "grid")
+        return FakeB7.b7_acq_score(self, gh[0], rh[0], kind, tradeoff, bound, sign, fmin, score_host, argmax, argmax_original, best, nan_count)
+
+
 class FakeError(Exception):
     pass

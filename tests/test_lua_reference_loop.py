@@ -270,3 +270,35 @@ def test_reference_example_script_variants(rt, extra, acq_calls):
     assert "Error" not in rt.out.getvalue()
     assert fake.calls.count("b7_sobol_generate") == 1 and fake.calls.count("b7_acq_score") == acq_calls
     assert fake.calls.count("b7_grid_remove") == (6 if acq_calls else 0)
+
+
+def test_reference_bot_with_nGPU_2_uses_the_multi_gpu_block(rt, oracle):
+    """config.bot.nGPU = 2 under the reference's bot: the glue creates one communicator, shards the host candidates over it, fits
+    through b7_gp_fit_sharded, scores through b7_acq_score_multi and removes through b7_grid_remove_sharded; the per-device factor
+    handles of every acquisition are freed, and the nominations equal those of the one-GPU bot on the same generator."""
+    I, fake = rt.I, rt.fake
+    LOOP = r"""
+local benchmarks = require('bot7.benchmarks')
+local hypers = {bot7.hyperparam('x1', 0, 1), bot7.hyperparam('x2', 0, 1)}
+local out = {}
+for _, n in ipairs{1, 2} do
+  torch.manualSeed(5)
+  local expt = {xDim = 2, yDim = 1, bot = {type = 'bo', nInitial = 2, budget = 6, nSamples = 2, verbose = 0, nGPU = n},
+                model = {noiseless = true}, grid = {type = 'sobol', size = 160}, score = {type = 'expected_improvement'}}
+  local bot = bot7.bots.bayesopt(benchmarks.braninhoo, hypers, expt)
+  for t = 1, 6 do bot:run_trial() end
+  out[n] = bot.observed:clone()
+  bot = nil
+  collectgarbage()
+end
+return out[1], out[2]
+"""
+    r = I.run(LOOP, "=nGPU loop")
+    assert np.array_equal(r[0].a, r[1].a) and r[0].a.shape == (6, 2)
+    calls = fake.calls
+    assert calls.count("b7_comm_init_all") == 1 and calls.count("b7_grid_from_host_sharded") == 1
+    assert calls.count("b7_gp_fit_sharded") == 4 and calls.count("b7_acq_score_multi") == 4 and calls.count("b7_grid_remove_sharded") == 6
+    import gc
+    gc.collect()
+    kinds = [f[0] for f in fake.freed]
+    assert kinds.count("gp") >= 8 + 4                                  # 2 per sharded acquisition, 1 per one-GPU acquisition (+ density handles)
