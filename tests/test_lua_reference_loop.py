@@ -194,6 +194,10 @@ for t = 1, 7 do
   bot:run_trial()
   CHECK(bot)
 end
+-- the reference's own bot:eval (bots/bayesopt.lua:56-82, not overridden by the glue) with the glue's model and score objects:
+-- per draw model:predict + score.compute through the library, summed and averaged by the reference code
+local sc = bot:eval()
+assert(sc:dim() == 1 and sc:size(1) == bot.candidates:size(1) and sc:eq(sc):all())
 return bot.observed, bot.responses, bot.model.hyp, bot.candidates:size(1)
 """, "=trial loop")
     obs, resp, hyp, n_left = r[0].a, r[1].a, r[2].a, r[3]
@@ -206,6 +210,7 @@ return bot.observed, bot.responses, bot.model.hyp, bot.candidates:size(1)
     assert len(set(rows)) == 7
     assert [s[2] for s in seen] == list(range(0, 8))
     assert fake.calls.count("b7_acq_score") == 5 and fake.calls.count("b7_grid_remove") == 7
+    assert fake.calls.count("b7_gp_predict") == 3 and fake.calls.count("b7_score_moments") == 3      # bot:eval, nSamples = 3
     assert fake.calls.count("b7_gp_refit") > 100                      # one device call per density evaluation of samplers/slice.lua
 
 
