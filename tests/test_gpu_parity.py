@@ -1057,3 +1057,13 @@ def test_nonfinite_hyper_parameters_return_instead_of_hanging(ctx, oracle):
     g = f.refit(hyp, L.FIT_LOGML_ONLY)                                  # and the handle still works
     assert abs(g.logml[1] - oracle.gp_fit(Xo, y, hyp[1], 0)["logml"]) <= 1e-9 * abs(ref)
     f.free()
+    # the same draw through the full fit (factor + inversion + slicing) and a prediction: returns, and the healthy draw is exact
+    t0 = time.perf_counter()
+    p = models.GPFactors(Xo, y, bad)
+    Xs = oracle.sobol_points(2, 64)
+    m0, v0 = p.predict(0, Xs)
+    m1, v1 = p.predict(1, Xs)
+    assert time.perf_counter() - t0 < 5.0
+    mr, vr = oracle.gp_predict(oracle.gp_fit(Xo, y, hyp[0], 0), Xs)
+    assert rel(m0, mr, 1.0) <= 1e-9 and m1.shape == (64,) and v1.shape == (64,)
+    p.free()
