@@ -363,6 +363,24 @@ return a, b, c, back
 
 
 @pytest.mark.gpu
+def test_lua_sobol_grid_equals_the_executed_reference(rt):
+    """The glue's grid class against the vectors the reference's own grids/sobol.lua produced under the interpreter
+    (tests/golden/ref_exec.npz): plain, skipped, two-sided rescale (done by the library) and the one-sided variants (done by the
+    glue's own tensor arithmetic, grids/sobol.lua:82-86) -- bit for bit."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_exec.npz"))
+    rt.set_global("MINS", rt.tensor(G["sobol_mins6"].reshape(1, -1)))            # 1 x d, as bots/abstract.lua builds them
+    rt.set_global("MAXES", rt.tensor(G["sobol_maxes6"].reshape(1, -1)))
+    r = rt.run(r"""
+local S = bot7.grids.sobol
+return S{size = 256, dims = 6}:generate(), S{size = 40, dims = 6, skip = 37}:generate(), S{size = 24, dims = 39}(),
+       S{size = 64, dims = 6, mins = MINS, maxes = MAXES}:generate(), S{size = 64, dims = 6, mins = MINS}:generate(),
+       S{size = 64, dims = 6, maxes = MAXES}:generate()
+""")
+    for got, key in zip(r, ["sobol_d6_n256", "sobol_d6_n40_skip37", "sobol_d39_n24", "sobol_d6_n64_scaled", "sobol_d6_n64_mins", "sobol_d6_n64_maxes"]):
+        assert np.array_equal(got.a, G[key]), key
+
+
+@pytest.mark.gpu
 def test_lua_scores_match_the_oracle(rt, oracle):
     g = np.random.default_rng(0)
     mean, var = g.standard_normal(4000), np.abs(g.standard_normal(4000)) * 0.3

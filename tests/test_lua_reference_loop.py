@@ -307,3 +307,22 @@ return out[1], out[2]
     gc.collect()
     kinds = [f[0] for f in fake.freed]
     assert kinds.count("gp") >= 8 + 4                                  # 2 per sharded acquisition, 1 per one-GPU acquisition (+ density handles)
+
+
+def test_glue_grid_class_reproduces_the_executed_reference_grids(rt):
+    """bot7.grids.sobol after install() (the glue class under the reference's grids/abstract.lua, unit-cube points from the
+    stand-in library) against the vectors of the reference's own generator (tests/golden/ref_exec.npz), including the one-sided
+    rescale variants that the glue computes with its own tensor arithmetic."""
+    I = rt.I
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_exec.npz"))
+    I.G.set("MINS", torch7.Tensor(np.ascontiguousarray(G["sobol_mins6"].reshape(1, -1)), "torch.DoubleTensor"))
+    I.G.set("MAXES", torch7.Tensor(np.ascontiguousarray(G["sobol_maxes6"].reshape(1, -1)), "torch.DoubleTensor"))
+    r = I.run(r"""
+local S = bot7.grids.sobol
+assert(torch.type(S{size = 1, dims = 2}) == 'bot7_b200.grids.sobol')
+return S{size = 256, dims = 6}:generate(), S{size = 40, dims = 6, skip = 37}:generate(), S{size = 24, dims = 39}(),
+       S{size = 64, dims = 6, mins = MINS, maxes = MAXES}:generate(), S{size = 64, dims = 6, mins = MINS}:generate(),
+       S{size = 64, dims = 6, maxes = MAXES}:generate()
+""")
+    for got, key in zip(r, ["sobol_d6_n256", "sobol_d6_n40_skip37", "sobol_d39_n24", "sobol_d6_n64_scaled", "sobol_d6_n64_mins", "sobol_d6_n64_maxes"]):
+        assert np.array_equal(got.a, G[key]), key
