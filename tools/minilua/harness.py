@@ -21,6 +21,7 @@ BOT7_FIXTURE = r"""
 bot7 = {grids = {}, scores = {}, models = {}, bots = {}, samplers = {}, utils = {}}
 do
   local g = torch.class('bot7.grids.abstract');   function g:__init() end
+  function g:__call__(config) return self:generate(config or self.config) end     -- grids/abstract.lua:24-27
   local s = torch.class('bot7.scores.abstract');  function s:__init() end
   local m = torch.class('bot7.models.abstract');  function m:__init() end
   function m:cache() return {} end
