@@ -583,6 +583,7 @@ def main():
                    "arithmetic": "fp64 results; on the int8_ozaki path the N^2 products are 28 exact int8 slice products recombined in fp64, the "
                                  "posterior mean is the fp64 dot product k*^T alpha",
                    "kernel": "ARD-SE", "candidates_per_gpu_per_step": cnt, "candidates_total": M_total,
+                   "e2e_candidates_per_gpu": int(m_e2e),
                    "grid": "Sobol (generated on device, per-rank shard)",
                    "l2": f"inputs larger than L2: {S} inverse factors = {S * slices_bytes_per_draw(Np) / 1e9:.2f} GB of int8 slices "
                          f"+ {min(cnt, SMS * 128) * Np * 7 / 1e6:.0f} MB K* panel per launch vs 126 MB L2",
